@@ -1,0 +1,92 @@
+"""ctypes binding of libhuffb200.so (the C ABI in include/huffman_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C huffman_b200/csrc`.
+There is no Python or CPU fallback: if the shared object is missing, loading raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
+
+HF_OK = 0
+ERR_NAMES = {
+    1: "HF_ERR_CUDA", 2: "HF_ERR_ARG", 3: "HF_ERR_CAPACITY", 4: "HF_ERR_FORMAT",
+    5: "HF_ERR_CODE_TOO_LONG", 6: "HF_ERR_INTERNAL", 7: "HF_ERR_IO",
+}
+NSYM = 65536
+
+
+class HuffmanError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+
+
+class CbInfo(ctypes.Structure):
+    _fields_ = [("n_unique", ctypes.c_uint32), ("max_code_bits", ctypes.c_uint32),
+                ("table_bits", ctypes.c_uint64), ("payload_bits", ctypes.c_uint64),
+                ("status", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class HeaderInfo(ctypes.Structure):
+    _fields_ = [("n_unique", ctypes.c_uint32), ("is_odd", ctypes.c_uint32),
+                ("last_byte", ctypes.c_uint32), ("max_code_bits", ctypes.c_uint32),
+                ("original_bytes", ctypes.c_uint64), ("payload_start_bit", ctypes.c_uint64),
+                ("status", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+# name -> (restype, argtypes); every symbol include/huffman_b200.h declares
+_P = ctypes.c_void_p
+_U64 = ctypes.c_uint64
+_SIGS = {
+    "hf_ctx_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, _P]),
+    "hf_ctx_destroy": (ctypes.c_int, [_P]),
+    "hf_ctx_set_stream": (ctypes.c_int, [_P, _P]),
+    "hf_sync": (ctypes.c_int, [_P]),
+    "hf_last_error": (ctypes.c_char_p, [_P]),
+    "hf_version": (ctypes.c_char_p, []),
+    "hf_launch_count": (_U64, [_P]),
+    "hf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t]),
+    "hf_host_free": (ctypes.c_int, [_P]),
+    "hf_codebook_bytes": (ctypes.c_size_t, []),
+    "hf_decode_table_bytes": (ctypes.c_size_t, []),
+    "hf_compress_bound": (_U64, [_U64]),
+    "hf_histogram": (ctypes.c_int, [_P, _P, _U64, _P]),
+    "hf_build_codebook": (ctypes.c_int, [_P, _P, _P]),
+    "hf_codebook_info": (ctypes.c_int, [_P, _P, ctypes.POINTER(CbInfo)]),
+    "hf_codebook_export": (ctypes.c_int, [_P, _P, _P, _P, _P]),
+    "hf_shard_payload_bits": (ctypes.c_int, [_P, _P, _P, _P]),
+    "hf_header_pack": (ctypes.c_int, [_P, _P, _U64, ctypes.c_uint32, _P, _U64]),
+    "hf_encode": (ctypes.c_int, [_P, _P, _U64, _P, _P, _U64]),
+    "hf_compress": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_parse_header": (ctypes.c_int, [_P, _P, _U64, _P, ctypes.POINTER(HeaderInfo)]),
+    "hf_decode_table_from_codebook": (ctypes.c_int, [_P, _P, _P]),
+    "hf_decode": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P]),
+    "hf_decompress": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_compress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_decompressed_size_host": (ctypes.c_int, [_P, _U64, ctypes.POINTER(_U64)]),
+    "hf_decompress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_archive_file": (ctypes.c_int, [_P, ctypes.c_char_p]),
+    "hf_extract_file": (ctypes.c_int, [_P, ctypes.c_char_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and attach signatures; raises if it was not built"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)         # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

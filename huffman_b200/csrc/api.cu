@@ -1,0 +1,567 @@
+// api.cu — the C ABI of libhuffb200 (include/huffman_b200.h): context, stage wrappers,
+// whole-file device calls, host-buffer pipelines and the two program-level entry points
+// that mirror the reference's mains (/root/reference/Compressor.cu:315-632,
+// /root/reference/Decompressor.cu:47-114).  No CPU fallback anywhere: without a usable
+// GPU every call returns HF_ERR_CUDA.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <dirent.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace hf {
+
+size_t codebook_alloc_bytes();          // codebook.cu
+
+int set_err(Ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int ensure_ws(Ctx *c, size_t bytes)
+{
+    if (bytes <= c->ws_bytes) return HF_OK;
+    size_t want = bytes + (bytes >> 2);
+    if (want < (96u << 20)) want = 96u << 20;
+    if (c->ws) HF_CUDA(c, cudaFree(c->ws));     // synchronises: no kernel still uses the old block
+    c->ws = nullptr; c->ws_bytes = 0;
+    HF_CUDA(c, cudaMalloc(&c->ws, want));
+    c->ws_bytes = want;
+    return HF_OK;
+}
+
+static int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes)
+{
+    if (bytes <= *have) return HF_OK;
+    if (*p) HF_CUDA(c, cudaFree(*p));
+    *p = nullptr; *have = 0;
+    HF_CUDA(c, cudaMalloc(p, bytes + 256));
+    *have = bytes;
+    return HF_OK;
+}
+
+static double now_ms()
+{
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    return tv.tv_sec * 1000.0 + tv.tv_usec / 1000.0;
+}
+
+static uint32_t preamble_bytes(uint64_t n) { return 3 + (uint32_t)(n & 1); }
+
+}  // namespace hf
+
+using namespace hf;
+
+#define CTX(c) reinterpret_cast<Ctx *>(c)
+#define NEED_CTX(c)                         \
+    if (!(c)) return HF_ERR_ARG;            \
+    do {                                    \
+        cudaError_t _e = cudaSetDevice(CTX(c)->device); \
+        if (_e != cudaSuccess) return set_err(CTX(c), HF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" {
+
+const char *hf_version(void) { return "huffman_b200 0.1 (sm_100a)"; }
+
+int hf_ctx_create(hf_ctx **out, int device, void *stream)
+{
+    if (!out) return HF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return HF_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return HF_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HF_ERR_CUDA;
+    if (prop.major < 10) return HF_ERR_CUDA;            // sm_100a code only
+    Ctx *c = (Ctx *)calloc(1, sizeof(Ctx));
+    if (!c) return HF_ERR_ARG;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { free(c); return HF_ERR_CUDA; }
+        c->own_stream = true;
+    }
+    bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_scratch, 4096) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_cb, codebook_alloc_bytes()) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_tab, sizeof(DecodeTable)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_hist, NSYM * 8 + 256) == cudaSuccess;
+    ok = ok && ensure_ws(c, 1) == HF_OK;
+    if (!ok) { hf_ctx_destroy(reinterpret_cast<hf_ctx *>(c)); return HF_ERR_CUDA; }
+    *out = reinterpret_cast<hf_ctx *>(c);
+    return HF_OK;
+}
+
+int hf_ctx_destroy(hf_ctx *ctx)
+{
+    if (!ctx) return HF_OK;
+    Ctx *c = CTX(ctx);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->ws) cudaFree(c->ws);
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->d_cb) cudaFree(c->d_cb);
+    if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    free(c);
+    return HF_OK;
+}
+
+int hf_ctx_set_stream(hf_ctx *ctx, void *stream)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)stream;
+    return HF_OK;
+}
+
+int hf_sync(hf_ctx *ctx)
+{
+    NEED_CTX(ctx);
+    HF_CUDA(CTX(ctx), cudaStreamSynchronize(CTX(ctx)->stream));
+    return HF_OK;
+}
+
+const char *hf_last_error(hf_ctx *ctx) { return ctx ? CTX(ctx)->err : "no context"; }
+uint64_t hf_launch_count(hf_ctx *ctx) { return ctx ? CTX(ctx)->launches : 0; }
+
+int hf_host_alloc(void **h_ptr, size_t bytes)
+{
+    if (!h_ptr) return HF_ERR_ARG;
+    return cudaMallocHost(h_ptr, bytes ? bytes : 1) == cudaSuccess ? HF_OK : HF_ERR_CUDA;
+}
+int hf_host_free(void *h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? HF_OK : HF_ERR_CUDA; }
+
+size_t hf_codebook_bytes(void) { return codebook_alloc_bytes(); }
+size_t hf_decode_table_bytes(void) { return sizeof(DecodeTable); }
+
+uint64_t hf_compress_bound(uint64_t n)
+{   // header: <= min(65536, n/2) entries of <= 11 bytes; payload: an optimal prefix code never
+    // exceeds the 16-bit fixed-length code, i.e. n bytes
+    uint64_t u = n / 2 < NSYM ? n / 2 : NSYM;
+    return 4 + 11 * u + 8 + n + 32;
+}
+
+// ---- compress stages ---------------------------------------------------------------
+int hf_histogram(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, uint64_t *d_hist)
+{
+    NEED_CTX(ctx);
+    if (!d_hist || (!d_in && n_bytes)) return set_err(CTX(ctx), HF_ERR_ARG, "hf_histogram: null pointer");
+    return launch_histogram(CTX(ctx), d_in, n_bytes, reinterpret_cast<unsigned long long *>(d_hist));
+}
+
+int hf_build_codebook(hf_ctx *ctx, const uint64_t *d_hist, void *d_codebook)
+{
+    NEED_CTX(ctx);
+    if (!d_hist || !d_codebook) return set_err(CTX(ctx), HF_ERR_ARG, "hf_build_codebook: null pointer");
+    return launch_codebook(CTX(ctx), reinterpret_cast<const unsigned long long *>(d_hist),
+                           reinterpret_cast<Codebook *>(d_codebook));
+}
+
+int hf_codebook_info(hf_ctx *ctx, const void *d_codebook, hf_cb_info_t *h_info)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!d_codebook || !h_info) return set_err(c, HF_ERR_ARG, "hf_codebook_info: null pointer");
+    Codebook *h = reinterpret_cast<Codebook *>(c->h_scratch);       // only the 48-byte summary is copied
+    HF_CUDA(c, cudaMemcpyAsync(h, d_codebook, offsetof(Codebook, order), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    h_info->n_unique = h->U;
+    h_info->max_code_bits = h->maxlen;
+    h_info->table_bits = h->table_bits;
+    h_info->payload_bits = h->payload_bits;
+    h_info->status = h->status;
+    h_info->reserved = 0;
+    return HF_OK;
+}
+
+int hf_codebook_export(hf_ctx *ctx, const void *d_codebook, uint16_t *h_order, uint8_t *h_len, uint64_t *h_code)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    const Codebook *cb = reinterpret_cast<const Codebook *>(d_codebook);
+    if (!cb) return set_err(c, HF_ERR_ARG, "hf_codebook_export: null pointer");
+    if (h_order) HF_CUDA(c, cudaMemcpyAsync(h_order, cb->order, sizeof(cb->order), cudaMemcpyDeviceToHost, c->stream));
+    if (h_len) HF_CUDA(c, cudaMemcpyAsync(h_len, cb->len, sizeof(cb->len), cudaMemcpyDeviceToHost, c->stream));
+    if (h_code) HF_CUDA(c, cudaMemcpyAsync(h_code, cb->code, sizeof(cb->code), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+int hf_shard_payload_bits(hf_ctx *ctx, const uint64_t *d_shard_hist, const void *d_codebook, uint64_t *d_bits)
+{
+    NEED_CTX(ctx);
+    if (!d_shard_hist || !d_codebook || !d_bits) return set_err(CTX(ctx), HF_ERR_ARG, "hf_shard_payload_bits: null pointer");
+    return launch_shard_bits(CTX(ctx), reinterpret_cast<const unsigned long long *>(d_shard_hist),
+                             reinterpret_cast<const Codebook *>(d_codebook),
+                             reinterpret_cast<unsigned long long *>(d_bits));
+}
+
+int hf_header_pack(hf_ctx *ctx, const void *d_codebook, uint64_t n_bytes, uint32_t last_byte, uint8_t *d_file,
+                   uint64_t capacity)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!d_codebook || !d_file) return set_err(c, HF_ERR_ARG, "hf_header_pack: null pointer");
+    uint64_t u = n_bytes / 2 < NSYM ? n_bytes / 2 : NSYM;
+    if (capacity < 4 + 11 * u + 8 + 4)
+        return set_err(c, HF_ERR_CAPACITY, "hf_header_pack: capacity %llu below the header bound %llu",
+                       (unsigned long long)capacity, (unsigned long long)(4 + 11 * u + 12));
+    return launch_header_pack(c, reinterpret_cast<const Codebook *>(d_codebook), n_bytes, last_byte, d_file, capacity);
+}
+
+int hf_encode(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, const void *d_codebook, uint8_t *d_stream,
+              uint64_t start_bit)
+{
+    NEED_CTX(ctx);
+    if ((!d_in && n_bytes) || !d_codebook || !d_stream) return set_err(CTX(ctx), HF_ERR_ARG, "hf_encode: null pointer");
+    return launch_encode(CTX(ctx), d_in, n_bytes, reinterpret_cast<const Codebook *>(d_codebook), d_stream, start_bit, 0);
+}
+
+// shared tail of hf_compress / hf_compress_host: codebook -> sizes -> header -> payload.
+// *h_last is read after the synchronisation inside hf_codebook_info.
+static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *h_last, uint8_t *d_file,
+                               uint64_t capacity, uint64_t *h_file_bytes)
+{
+    hf_ctx *ctx = reinterpret_cast<hf_ctx *>(c);
+    Codebook *cb = reinterpret_cast<Codebook *>(c->d_cb);
+    int rc = launch_codebook(c, reinterpret_cast<unsigned long long *>(c->d_hist), cb);
+    if (rc) return rc;
+    hf_cb_info_t info;
+    rc = hf_codebook_info(ctx, cb, &info);
+    if (rc) return rc;
+    if (info.status) return set_err(c, (int)info.status, "codebook: a code word is longer than 64 bits");
+    const uint64_t bits = info.table_bits + 64 + info.payload_bits;
+    const uint64_t total = preamble_bytes(n) + (bits + 7) / 8;
+    if (h_file_bytes) *h_file_bytes = total;
+    if (total > capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_compress: need %llu bytes, capacity %llu", (unsigned long long)total,
+                       (unsigned long long)capacity);
+    rc = hf_header_pack(ctx, cb, n, (n & 1) ? *h_last : 0, d_file, capacity);
+    if (rc) return rc;
+    return launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64,
+                         info.max_code_bits ? info.max_code_bits : 1);
+}
+
+int hf_compress(hf_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_file, uint64_t capacity,
+                uint64_t *h_file_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if ((!d_in && n) || !d_file) return set_err(c, HF_ERR_ARG, "hf_compress: null pointer");
+    HF_CUDA(c, cudaMemsetAsync(c->d_hist, 0, NSYM * 8, c->stream));
+    int rc = launch_histogram(c, d_in, n, reinterpret_cast<unsigned long long *>(c->d_hist));
+    if (rc) return rc;
+    uint8_t *h_last = reinterpret_cast<uint8_t *>(c->h_scratch) + 2048;
+    *h_last = 0;
+    if (n & 1) HF_CUDA(c, cudaMemcpyAsync(h_last, d_in + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    rc = compress_after_hist(c, d_in, n, h_last, d_file, capacity, h_file_bytes);
+    if (rc) return rc;
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+// ---- decompress stages -------------------------------------------------------------
+int hf_parse_header(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, void *d_decode_table,
+                    hf_header_info_t *h_info)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!d_file || !d_decode_table || !h_info) return set_err(c, HF_ERR_ARG, "hf_parse_header: null pointer");
+    if (file_bytes < 11) return set_err(c, HF_ERR_FORMAT, "hf_parse_header: %llu bytes is shorter than any image",
+                                        (unsigned long long)file_bytes);
+    // device-side info block lives at the end of the hist buffer's allocation
+    hf_header_info_t *d_info = reinterpret_cast<hf_header_info_t *>((uint8_t *)c->d_hist + NSYM * 8);
+    DecodeTable *tab = reinterpret_cast<DecodeTable *>(d_decode_table);
+    int rc = launch_parse_header(c, d_file, file_bytes, tab, d_info);
+    if (rc) return rc;
+    hf_header_info_t *h = reinterpret_cast<hf_header_info_t *>((uint8_t *)c->h_scratch + 1024);
+    uint32_t *h_tab = reinterpret_cast<uint32_t *>((uint8_t *)c->h_scratch + 1536);
+    HF_CUDA(c, cudaMemcpyAsync(h, d_info, sizeof(hf_header_info_t), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaMemcpyAsync(h_tab, tab, 48, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *h_info = *h;
+    h_info->max_code_bits = h_tab[1];
+    if (h_tab[6] != 0 && h_info->status == HF_OK) h_info->status = h_tab[6];
+    if (h_info->status) return set_err(c, HF_ERR_FORMAT, "hf_parse_header: malformed header");
+    return HF_OK;
+}
+
+int hf_decode_table_from_codebook(hf_ctx *ctx, const void *d_codebook, void *d_decode_table)
+{
+    NEED_CTX(ctx);
+    if (!d_codebook || !d_decode_table) return set_err(CTX(ctx), HF_ERR_ARG, "hf_decode_table_from_codebook: null pointer");
+    return launch_table_from_codebook(CTX(ctx), reinterpret_cast<const Codebook *>(d_codebook),
+                                      reinterpret_cast<DecodeTable *>(d_decode_table));
+}
+
+int hf_decode(hf_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
+              const void *d_decode_table, uint8_t *d_out)
+{
+    NEED_CTX(ctx);
+    if (!d_decode_table || (n_symbols && (!d_stream || !d_out))) return set_err(CTX(ctx), HF_ERR_ARG, "hf_decode: null pointer");
+    return launch_decode(CTX(ctx), d_stream, stream_bytes, start_bit, n_symbols,
+                         reinterpret_cast<const DecodeTable *>(d_decode_table), d_out);
+}
+
+// flags written by the decode kernels (decode.cu: DecWork.flags) sit at ws + 8 MiB
+static int check_decode_flags(Ctx *c)
+{
+    unsigned long long *h = reinterpret_cast<unsigned long long *>((uint8_t *)c->h_scratch + 3072);
+    HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + (8u << 20), 32, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[1]) return set_err(c, HF_ERR_FORMAT, "hf_decode: the payload holds bits that are no code word");
+    return HF_OK;
+}
+
+int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8_t *d_out, uint64_t capacity,
+                  uint64_t *h_out_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    hf_header_info_t info;
+    int rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);
+    if (rc) return rc;
+    if (h_out_bytes) *h_out_bytes = info.original_bytes;
+    if (info.original_bytes > capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_decompress: need %llu bytes, capacity %llu",
+                       (unsigned long long)info.original_bytes, (unsigned long long)capacity);
+    if (info.original_bytes && !d_out) return set_err(c, HF_ERR_ARG, "hf_decompress: null output");
+    const uint64_t nsym = info.original_bytes / 2;
+    if (nsym) {
+        rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, reinterpret_cast<DecodeTable *>(c->d_tab), d_out);
+        if (rc) return rc;
+    }
+    if (info.is_odd) HF_CUDA(c, cudaMemsetAsync(d_out + info.original_bytes - 1, (int)info.last_byte, 1, c->stream));   // D:286-289
+    if (nsym) return check_decode_flags(c);
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+// ---- host-buffer calls ---------------------------------------------------------------
+static const uint64_t H2D_CHUNK = 32ull << 20;
+
+int hf_compress_host(hf_ctx *ctx, const uint8_t *h_in, uint64_t n, uint8_t *h_file, uint64_t capacity,
+                     uint64_t *h_file_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if ((!h_in && n) || !h_file) return set_err(c, HF_ERR_ARG, "hf_compress_host: null pointer");
+    const uint64_t bound = hf_compress_bound(n);
+    int rc = ensure_buf(c, &c->d_in, &c->d_in_bytes, n + 16);
+    if (rc) return rc;
+    rc = ensure_buf(c, &c->d_out, &c->d_out_bytes, bound + 16);
+    if (rc) return rc;
+    uint8_t *d_in = reinterpret_cast<uint8_t *>(c->d_in);
+    // the image starts 16 - preamble bytes into the buffer so that the bit stream is 16-byte aligned
+    uint8_t *d_file = reinterpret_cast<uint8_t *>(c->d_out) + (16 - preamble_bytes(n));
+    unsigned long long *d_hist = reinterpret_cast<unsigned long long *>(c->d_hist);
+
+    HF_CUDA(c, cudaMemsetAsync(d_hist, 0, NSYM * 8, c->stream));
+    // copy chunk k on the copy stream while the histogram of chunk k-1 runs
+    HF_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    HF_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0));
+    int e = 0;
+    for (uint64_t o = 0; o < n; o += H2D_CHUNK) {
+        uint64_t len = n - o < H2D_CHUNK ? n - o : H2D_CHUNK;
+        HF_CUDA(c, cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, c->copy_stream));
+        cudaEvent_t ev = c->ev[1 + (e++ % 6)];
+        HF_CUDA(c, cudaEventRecord(ev, c->copy_stream));
+        HF_CUDA(c, cudaStreamWaitEvent(c->stream, ev, 0));
+        rc = launch_histogram(c, d_in + o, len & ~1ull, d_hist);     // chunks are even-sized; the odd last byte is not a symbol
+        if (rc) return rc;
+    }
+    uint64_t total = 0;
+    rc = compress_after_hist(c, d_in, n, n ? h_in + n - 1 : nullptr, d_file, bound, &total);
+    if (h_file_bytes) *h_file_bytes = total;
+    if (rc) return rc;
+    if (total > capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_compress_host: need %llu bytes, capacity %llu", (unsigned long long)total,
+                       (unsigned long long)capacity);
+    HF_CUDA(c, cudaMemcpyAsync(h_file, d_file, total, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+int hf_decompressed_size_host(const uint8_t *h_file, uint64_t file_bytes, uint64_t *h_out_bytes)
+{
+    // walks the header on the host just far enough to find the 64-bit size (D:68-103, D:243-255);
+    // used by callers to size the output buffer before the GPU call
+    if (!h_file || !h_out_bytes || file_bytes < 11) return HF_ERR_FORMAT;
+    uint32_t U = (uint32_t)h_file[0] | ((uint32_t)h_file[1] << 8);
+    uint32_t pre = 3 + (h_file[2] != 0);
+    if (U == 0) U = (file_bytes - pre == 8) ? 0 : 65536;
+    const uint8_t *s = h_file + pre;
+    uint64_t nb = file_bytes - pre, pos = 0;
+    auto byte_at = [&](uint64_t bit) -> uint32_t {
+        uint64_t i = bit >> 3;
+        uint32_t sh = (uint32_t)(bit & 7);
+        uint32_t a = i < nb ? s[i] : 0, b = i + 1 < nb ? s[i + 1] : 0;
+        return (((a << 8) | b) >> (8 - sh)) & 0xFF;
+    };
+    for (uint32_t k = 0; k < U; k++) {
+        if ((pos >> 3) + 3 > nb) return HF_ERR_FORMAT;
+        uint32_t len = byte_at(pos + 16);
+        if (len == 0 && U > 1) return HF_ERR_FORMAT;
+        pos += 24 + len;
+    }
+    if ((pos + 64 + 7) / 8 > nb) return HF_ERR_FORMAT;
+    uint64_t n = 0;
+    for (int i = 0; i < 8; i++) n |= (uint64_t)byte_at(pos + 8 * i) << (8 * i);
+    *h_out_bytes = n;
+    return HF_OK;
+}
+
+int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, uint8_t *h_out, uint64_t capacity,
+                       uint64_t *h_out_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!h_file) return set_err(c, HF_ERR_ARG, "hf_decompress_host: null pointer");
+    if (file_bytes < 11) return set_err(c, HF_ERR_FORMAT, "hf_decompress_host: image too short");
+    int rc = ensure_buf(c, &c->d_out, &c->d_out_bytes, file_bytes + 32);
+    if (rc) return rc;
+    uint8_t *d_file = reinterpret_cast<uint8_t *>(c->d_out);
+    HF_CUDA(c, cudaMemcpyAsync(d_file, h_file, file_bytes, cudaMemcpyHostToDevice, c->stream));
+    hf_header_info_t info;
+    rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);
+    if (rc) return rc;
+    if (h_out_bytes) *h_out_bytes = info.original_bytes;
+    if (info.original_bytes > capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_decompress_host: need %llu bytes, capacity %llu",
+                       (unsigned long long)info.original_bytes, (unsigned long long)capacity);
+    if (info.original_bytes && !h_out) return set_err(c, HF_ERR_ARG, "hf_decompress_host: null output");
+    rc = ensure_buf(c, &c->d_in, &c->d_in_bytes, info.original_bytes + 16);
+    if (rc) return rc;
+    uint8_t *d_out = reinterpret_cast<uint8_t *>(c->d_in);
+    const uint64_t nsym = info.original_bytes / 2;
+    if (nsym) {
+        rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, reinterpret_cast<DecodeTable *>(c->d_tab), d_out);
+        if (rc) return rc;
+        HF_CUDA(c, cudaMemcpyAsync(h_out, d_out, nsym * 2, cudaMemcpyDeviceToHost, c->stream));
+        rc = check_decode_flags(c);
+        if (rc) return rc;
+    }
+    if (info.is_odd) h_out[info.original_bytes - 1] = (uint8_t)info.last_byte;      // D:286-289
+    return HF_OK;
+}
+
+// ---- program-level entry points ------------------------------------------------------
+static bool file_exists(const std::string &name)
+{   // D:222-240: a file or a directory of that name
+    FILE *fp = fopen(name.c_str(), "rb");
+    if (fp) { fclose(fp); return true; }
+    DIR *d = opendir(name.c_str());
+    if (d) { closedir(d); return true; }
+    return false;
+}
+
+int hf_archive_file(hf_ctx *ctx, const char *path)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    FILE *f = fopen(path, "rb");
+    if (!f) {                                                   // C:325-330
+        printf("%s file does not exist\nProcess has been terminated\n", path);
+        return HF_OK;
+    }
+    fseek(f, 0, SEEK_END);
+    const uint64_t n = (uint64_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    printf("The size of the sum of ORIGINAL files is: %llu bytes\n", (unsigned long long)n);   // C:335
+    uint8_t *h_in = nullptr, *h_out = nullptr;
+    const uint64_t bound = hf_compress_bound(n);
+    if (hf_host_alloc((void **)&h_in, n + 1) || hf_host_alloc((void **)&h_out, bound)) {
+        fclose(f);
+        if (h_in) hf_host_free(h_in);
+        return set_err(c, HF_ERR_CUDA, "hf_archive_file: pinned allocation failed");
+    }
+    size_t got = n ? fread(h_in, 1, n, f) : 0;
+    fclose(f);
+    int rc = got == n ? HF_OK : set_err(c, HF_ERR_IO, "hf_archive_file: short read");
+    uint64_t total = 0;
+    if (!rc) {
+        double t0 = now_ms();
+        rc = hf_compress_host(ctx, h_in, n, h_out, bound, &total);
+        double t1 = now_ms();
+        if (!rc) {
+            hf_cb_info_t info;
+            hf_codebook_info(ctx, c->d_cb, &info);
+            printf("Unique symbols count: %u\n", info.n_unique);                            // C:385
+            printf("Histograming, construction and Encoding took %.3f ms\n", t1 - t0);
+        }
+    }
+    if (!rc) {
+        std::string outp = std::string(path) + ".compressed";                              // C:427-429
+        FILE *o = fopen(outp.c_str(), "wb");
+        if (!o || fwrite(h_out, 1, total, o) != total) rc = set_err(c, HF_ERR_IO, "hf_archive_file: cannot write %s", outp.c_str());
+        if (o) fclose(o);
+        if (!rc) {
+            printf("The size of the COMPRESSED file is: %llu bytes\n", (unsigned long long)total);      // C:612
+            printf("Compressed file's size is [%g%%] of the original files.\n", 100.0f * (float)total / (float)n);   // C:616-619
+            if (total > n) printf("\nWARNING: The compressed file's size is larger than the sum of the originals.\n\n");
+            printf("\nCreated compressed file: %s\nCompression is complete\n", outp.c_str());  // C:629-631
+        }
+    }
+    hf_host_free(h_in);
+    hf_host_free(h_out);
+    return rc;
+}
+
+int hf_extract_file(hf_ctx *ctx, const char *path)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    FILE *f = fopen(path, "rb");
+    if (!f) { printf("%s does not exist\n", path); return HF_OK; }      // D:59-63
+    fseek(f, 0, SEEK_END);
+    const uint64_t nb = (uint64_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    uint8_t *h_file = nullptr, *h_out = nullptr;
+    if (hf_host_alloc((void **)&h_file, nb + 1)) { fclose(f); return set_err(c, HF_ERR_CUDA, "hf_extract_file: pinned allocation failed"); }
+    size_t got = nb ? fread(h_file, 1, nb, f) : 0;
+    fclose(f);
+    int rc = got == nb ? HF_OK : set_err(c, HF_ERR_IO, "hf_extract_file: short read");
+    uint64_t n = 0;
+    if (!rc && hf_decompressed_size_host(h_file, nb, &n)) rc = set_err(c, HF_ERR_FORMAT, "hf_extract_file: malformed header");
+    if (!rc && hf_host_alloc((void **)&h_out, n + 1)) rc = set_err(c, HF_ERR_CUDA, "hf_extract_file: pinned allocation failed");
+    if (!rc) rc = hf_decompress_host(ctx, h_file, nb, h_out, n, &n);
+    if (!rc) {
+        std::string name = "DECOMPRESSED_FILE";                                             // D:104
+        if (file_exists(name)) {                                                            // D:185-219
+            for (int k = 1; k < 10; k++) {
+                name = "DECOMPRESSED_FILE(" + std::to_string(k) + ")";
+                if (!file_exists(name)) break;
+            }
+        }
+        FILE *o = fopen(name.c_str(), "wb");
+        if (!o || (n && fwrite(h_out, 1, n, o) != n)) rc = set_err(c, HF_ERR_IO, "hf_extract_file: cannot write %s", name.c_str());
+        if (o) fclose(o);
+        if (!rc) printf("Decompression is complete\n");                                     // D:113
+    }
+    hf_host_free(h_file);
+    if (h_out) hf_host_free(h_out);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// common.cuh — shared declarations of libhuffb200 (sm_100a only).
+// Layouts here are private to the library; include/huffman_b200.h is the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/huffman_b200.h"
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "libhuffb200 is written for sm_100a (B200) only"
+#endif
+
+namespace hf {
+
+constexpr uint32_t NSYM = HF_NSYM;
+
+// ---- device-resident codebook (hf_codebook_bytes) ---------------------------------
+// enc32: (len << 27) | code for len <= 26, the encoder's one-gather fast table.
+constexpr uint32_t ENC32_MAX_LEN = 26;
+struct Codebook {
+    uint32_t U;
+    uint32_t maxlen;
+    unsigned long long table_bits;
+    unsigned long long payload_bits;
+    uint32_t status;
+    uint32_t pad0;
+    unsigned long long pad1;
+    uint16_t order[NSYM];      // rank -> symbol, ascending (count, symbol)
+    uint8_t len[NSYM];         // by symbol, 0 when absent
+    uint32_t enc32[NSYM];      // by symbol
+    unsigned long long code[NSYM];   // by symbol, right aligned, root->leaf
+};
+
+// ---- device-resident decode tables (hf_decode_table_bytes) ------------------------
+// Level 1: K1-bit direct table (copied to shared memory by the decode kernels).
+//   leaf    (sym << 8) | len              1 <= len <= K1, bit 7 clear
+//   sub     (off << 8) | 0x80 | sub_bits  -> 2^sub_bits entries at t2[off]
+//   0       hole (incomplete code)
+// Level 2: per-prefix direct tables, sub_bits <= k2cap (12, or 8 when 12 would overflow t2).
+//   leaf    (sym << 8) | total_len
+//   0xFFFFFFFF  escape: the code is longer than K1 + sub_bits -> linear list `longs`
+constexpr uint32_t K1 = 12;
+constexpr uint32_t K2MAX = 12;
+constexpr uint32_t T2_CAP = 1u << 20;          // entries; 2^K1 prefixes x 2^8 always fits
+struct LongCode {
+    unsigned long long code_left;               // left aligned in 64 bits
+    uint32_t len;
+    uint32_t sym;
+};
+struct DecodeTable {
+    uint32_t U;
+    uint32_t maxlen;
+    uint32_t minlen;
+    uint32_t len_gcd;          // gcd of all code lengths: code word boundaries are start + k*gcd
+    uint32_t n_long;
+    uint32_t t2_used;
+    uint32_t status;
+    uint32_t single_sym;       // 0x10000 | sym when U == 1 with a zero-length code
+    uint32_t k2cap;
+    uint32_t pad[3];
+    uint32_t t1[1u << K1];
+    uint32_t sub_depth[1u << K1];
+    uint32_t t2[T2_CAP];
+    LongCode longs[NSYM];
+};
+
+// ---- context ----------------------------------------------------------------------
+struct Ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    uint64_t launches;
+    char err[512];
+    // workspace (device), grown on demand
+    void *ws;
+    size_t ws_bytes;
+    // small pinned host scratch for summaries
+    void *h_scratch;
+    // second stream + events for the host-buffer pipelines
+    cudaStream_t copy_stream;
+    cudaEvent_t ev[8];
+    // cached device buffers for the host-facing calls
+    void *d_in; size_t d_in_bytes;
+    void *d_out; size_t d_out_bytes;
+    void *d_cb;
+    void *d_tab;
+    void *d_hist;
+};
+
+int set_err(Ctx *c, int code, const char *fmt, ...);
+int ensure_ws(Ctx *c, size_t bytes);
+
+#define HF_CUDA(ctx, call)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return hf::set_err((ctx), HF_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                               cudaGetErrorString(_e));                                 \
+    } while (0)
+
+#define HF_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        HF_CUDA((ctx), cudaGetLastError());                                             \
+    } while (0)
+
+// ---- stage launchers (each in its own .cu) ------------------------------------------
+int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned long long *d_hist);
+int launch_codebook(Ctx *c, const unsigned long long *d_hist, Codebook *d_cb);
+int launch_shard_bits(Ctx *c, const unsigned long long *d_hist, const Codebook *d_cb,
+                      unsigned long long *d_bits);
+int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t last_byte,
+                       uint8_t *d_file, uint64_t capacity);
+int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb,
+                  uint8_t *d_stream, uint64_t start_bit, uint32_t maxlen_hint);
+int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, DecodeTable *d_tab,
+                        hf_header_info_t *d_info);
+int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab);
+int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
+                  uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out);
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 ld_stream_v4(const void *p)
+{   // streaming 128-bit load: read once, keep out of L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
+#endif
+
+}  // namespace hf

@@ -1,0 +1,815 @@
+// decode.cu — GPU decompressor: header parse, decode-table build, self-synchronising
+// subsequence decode.  The reference has NO GPU decoder: its Decompressor.cu is a host
+// program that fread()s one byte at a time and walks a pointer tree one bit at a time
+// (/root/reference/Decompressor.cu:68-103, :129-182, :243-291).  Its format carries no
+// gap / offset array, so parallel decode must find code word boundaries
+// by itself.
+//
+// Header (dec_parse_kernel): entry k+1 starts 24+len_k bits after entry k — a serial chain.
+//   One warp chases it SPECULATIVELY from shared-memory staging: lane j assumes the next
+//   entries keep the current stride and reads the length of entry k+j; the ballot of the
+//   first mismatch confirms up to 32 entries per step (the table is sorted by count, so
+//   lengths come in long runs).  Any header parses correctly, sorted ones ~32x faster.
+//
+// Tables (dt_*): 12-bit primary table in shared memory, per-prefix secondary tables (up to
+//   +12 bits) in global memory (L1/L2 resident), a linear list for still longer codes.
+//
+// Payload: chunks of 512 subsequences x 256 bits.
+//   A dec_sync_kernel   — every thread decodes its subsequence from the first position a code
+//       word can start at (exact when all code lengths share a gcd > 1, e.g. fixed-length
+//       codes), remembering the boundaries it met in its first 64 bits.  The true start is
+//       the predecessor's overflow; a thread re-synchronises by decoding from there only
+//       until it lands on a remembered boundary (a few code words).  Iterates to a fixed
+//       point inside the CTA.  Emits (start, count) per subsequence: 2 bytes per 32.
+//   B dec_fix_kernel    — one thread per chunk repairs the first subsequences from the true
+//       chunk start (the previous chunk's overflow); dec_fix_serial_kernel handles streams
+//       that fail to synchronise inside a whole chunk (correct, slow, practically never).
+//   S dec_scan_kernel   — exclusive scan of the chunk symbol counts.
+//   C dec_write_kernel  — decodes again from the known starts into a shared staging window
+//       and writes the symbols with aligned 128-bit stores.
+//
+// Algorithmic bytes: C read + N written (the payload is read twice: traffic ~ 2C + N).
+#include "common.cuh"
+
+namespace hf {
+
+constexpr int DEC_THREADS = 512;
+constexpr uint32_t SUB_BITS = 256;                              // bits per subsequence (thread)
+constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits = 16 KiB
+constexpr uint32_t CHUNK_WORDS = CHUNK_BITS / 32;               // 4096
+constexpr uint32_t CHUNK_PAD_WORDS = 8;                         // look-ahead past the chunk
+constexpr uint32_t WIN_SYMS = 16384;                            // output staging window (symbols)
+
+constexpr uint32_t E_SUB = 0x80u;                               // entry flag: sub-table / escape
+constexpr uint32_t E_ESCAPE = 0xFFFFFFFFu;
+
+struct DecWork {
+    unsigned long long flags[4];        // [0] any chunk failed to sync, [1] invalid code met, [2] table error
+    // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32, chunkE2[nch] u32 (0xFFFFFFFF = unchanged),
+    //              info[nch * DEC_THREADS] u16
+};
+
+struct DecLayout {
+    unsigned long long *chunkBase;
+    uint32_t *chunkCnt, *chunkE, *chunkE2;
+    uint16_t *info;
+    static size_t bytes(uint64_t nch) { return sizeof(DecWork) + nch * (8 + 4 + 4 + 4 + 2 * (size_t)DEC_THREADS); }
+    __host__ __device__ DecLayout(DecWork *w, uint64_t nch)
+    {
+        uint8_t *p = reinterpret_cast<uint8_t *>(w + 1);
+        chunkBase = reinterpret_cast<unsigned long long *>(p); p += nch * 8;
+        chunkCnt = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        chunkE = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        chunkE2 = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        info = reinterpret_cast<uint16_t *>(p);
+    }
+};
+
+// -----------------------------------------------------------------------------------
+// bit access.  Fetch functors return big-endian 32-bit word i of some bit string.
+struct SmemFetch {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return w[i]; }
+};
+struct GlobalFetch {                    // frame words straight from global memory, zero past the end
+    const uint8_t *frame;
+    unsigned long long frame_bytes;
+    unsigned long long word0;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const
+    {
+        unsigned long long b = (word0 + i) * 4ull;
+        if (b + 4 <= frame_bytes) return bswap32(*reinterpret_cast<const uint32_t *>(frame + b));
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++)
+            if (b + k < frame_bytes) v |= (uint32_t)frame[b + k] << (24 - 8 * k);
+        return v;
+    }
+};
+
+template <typename F>
+struct BitReader {
+    F f;
+    uint32_t wi;                        // next word to pull
+    unsigned long long win;             // upcoming bits, left aligned
+    uint32_t avail;                     // valid bits in win (kept > 32)
+    __device__ __forceinline__ void init(uint32_t bitpos)
+    {
+        wi = bitpos >> 5;
+        uint32_t sh = bitpos & 31;
+        win = (((unsigned long long)f(wi) << 32) | f(wi + 1)) << sh;
+        avail = 64 - sh;
+        wi += 2;
+        if (avail <= 32) { win |= (unsigned long long)f(wi++) << (32 - avail); avail += 32; }
+    }
+    __device__ __forceinline__ void consume(uint32_t n)     // n <= 32 per call
+    {
+        win <<= n;
+        avail -= n;
+        if (avail <= 32) { win |= (unsigned long long)f(wi++) << (32 - avail); avail += 32; }
+    }
+    __device__ __forceinline__ void skip(uint32_t n)
+    {
+        while (n > 32) { consume(32); n -= 32; }
+        consume(n);
+    }
+};
+
+template <typename F>
+__device__ __forceinline__ unsigned long long peek64(const F &f, uint32_t bitpos)
+{
+    uint32_t i = bitpos >> 5, sh = bitpos & 31;
+    unsigned long long hi = ((unsigned long long)f(i) << 32) | f(i + 1);
+    if (sh == 0) return hi;
+    return (hi << sh) | ((unsigned long long)f(i + 2) >> (32 - sh));
+}
+
+struct TabView {
+    const uint32_t *t1;                 // shared (kernels A, C) or global (kernel B)
+    const uint32_t *t2;
+    const LongCode *longs;
+    uint32_t n_long;
+};
+
+// one code word at the reader's position; returns (sym << 8) | len, len >= 1
+template <typename F>
+__device__ __forceinline__ uint32_t decode_one(const TabView &T, const BitReader<F> &r, uint32_t bitpos,
+                                               uint32_t &bad)
+{
+    uint32_t e = T.t1[(uint32_t)(r.win >> (64 - K1))];
+    if (e & E_SUB) {
+        if (e != E_ESCAPE) {
+            uint32_t sb = e & 31u;
+            uint32_t idx2 = (uint32_t)((r.win << K1) >> (64 - sb));
+            e = __ldg(&T.t2[(e >> 8) + idx2]);
+        }
+        if (e == E_ESCAPE) {            // longer than K1 + sub bits: scan the long-code list
+            unsigned long long w64 = peek64(r.f, bitpos);
+            e = 0;
+            for (uint32_t i = 0; i < T.n_long; i++) {
+                LongCode lc = T.longs[i];
+                if (((w64 ^ lc.code_left) >> (64 - lc.len)) == 0) { e = (lc.sym << 8) | lc.len; break; }
+            }
+        }
+    }
+    if (e == 0) { bad = 1; e = 1; }     // hole in the code: flag it, step one bit so the walk ends
+    return e;
+}
+
+// -----------------------------------------------------------------------------------
+// decode-table build from (sym, len, code)[U]
+struct TabSrc {                         // workspace arrays filled by the header parser or from a Codebook
+    uint32_t sym[NSYM];
+    uint32_t len[NSYM];
+    unsigned long long code[NSYM];
+    unsigned long long entry_pos[NSYM];
+    unsigned long long len_mask[2];     // bit (len-1) set for every length in use
+    uint32_t U;
+    uint32_t pad;
+};
+
+__global__ void dt_from_codebook_kernel(const Codebook *__restrict__ cb, TabSrc *__restrict__ src)
+{
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) src->U = cb->U;
+    if (k < cb->U) {
+        uint32_t s = cb->order[k];
+        src->sym[k] = s; src->len[k] = cb->len[s]; src->code[k] = cb->code[s];
+    }
+}
+
+__global__ void dt_depth_kernel(const TabSrc *__restrict__ src, DecodeTable *__restrict__ tab,
+                                unsigned long long *len_mask)
+{
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t U = src->U;
+    if (k >= U) return;
+    uint32_t len = src->len[k];
+    if (len == 0 || len > 64) { if (!(U == 1 && len == 0)) atomicExch(&tab->status, (uint32_t)HF_ERR_FORMAT); return; }
+    atomicOr(len_mask, 1ull << (len - 1));
+    if (len > K1) atomicMax(&tab->sub_depth[(uint32_t)(src->code[k] >> (len - K1))], len - K1);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+dt_offsets_kernel(const TabSrc *__restrict__ src, DecodeTable *__restrict__ tab, const unsigned long long *len_mask)
+{
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_cap;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (1u << K1) / 1024;     // 4 prefixes per thread
+    uint32_t cap = K2MAX;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        uint32_t sz[per], sum = 0;
+        for (uint32_t j = 0; j < per; j++) {
+            uint32_t d = tab->sub_depth[tid * per + j];
+            sz[j] = d ? (1u << min(d, cap)) : 0u;
+            sum += sz[j];
+        }
+        uint32_t x = sum;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t s = s_w[lane], t = s;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+            s_w[lane] = t - s;
+            if (lane == 31) s_w[32] = t;
+        }
+        __syncthreads();
+        uint32_t total = s_w[32];
+        if (total > T2_CAP && attempt == 0) { cap = 8; __syncthreads(); continue; }   // 2^12 * 2^8 always fits
+        uint32_t run = x - sum + s_w[wid];
+        for (uint32_t j = 0; j < per; j++) {
+            uint32_t p = tid * per + j;
+            uint32_t d = tab->sub_depth[p];
+            if (d) { tab->t1[p] = (run << 8) | E_SUB | min(d, cap); run += sz[j]; }
+        }
+        if (tid == 0) { tab->t2_used = total; s_cap = cap; }
+        break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long m = len_mask[0];
+        uint32_t U = src->U;
+        tab->U = U;
+        uint32_t g = 0, mn = 0, mx = 0;
+        for (uint32_t l = 1; l <= 64; l++)
+            if ((m >> (l - 1)) & 1) {
+                if (!mn) mn = l;
+                mx = l;
+                uint32_t a = g, b = l;                  // gcd(g, l); gcd(0, l) = l
+                while (b) { uint32_t t = a % b; a = b; b = t; }
+                g = a;
+            }
+        tab->maxlen = mx; tab->minlen = mn; tab->len_gcd = g ? g : 1;
+        tab->n_long = 0;
+        tab->single_sym = (U == 1 && src->len[0] == 0) ? (0x10000u | src->sym[0]) : 0u;
+        tab->k2cap = s_cap;
+    }
+}
+
+__global__ void dt_fill_kernel(const TabSrc *__restrict__ src, DecodeTable *__restrict__ tab)
+{
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= src->U) return;
+    uint32_t len = src->len[k], sym = src->sym[k];
+    unsigned long long code = src->code[k];
+    if (len == 0 || len > 64) return;
+    const uint32_t leaf = (sym << 8) | len;
+    if (len <= K1) {
+        uint32_t base = (uint32_t)code << (K1 - len), n = 1u << (K1 - len);
+        for (uint32_t i = 0; i < n; i++) tab->t1[base + i] = leaf;
+        return;
+    }
+    uint32_t p = (uint32_t)(code >> (len - K1));
+    uint32_t e1 = tab->t1[p];
+    uint32_t sb = e1 & 31u, off = e1 >> 8;
+    uint32_t rem = len - K1;
+    if (rem <= sb) {
+        uint32_t low = (uint32_t)(code & ((1ull << rem) - 1));
+        uint32_t base = low << (sb - rem), n = 1u << (sb - rem);
+        for (uint32_t i = 0; i < n; i++) tab->t2[off + base + i] = leaf;
+    } else {
+        uint32_t idx = (uint32_t)((code >> (rem - sb)) & ((1u << sb) - 1));
+        tab->t2[off + idx] = E_ESCAPE;
+        uint32_t slot = atomicAdd(&tab->n_long, 1u);
+        LongCode lc;
+        lc.code_left = code << (64 - len);
+        lc.len = len; lc.sym = sym;
+        tab->longs[slot] = lc;
+    }
+}
+
+// -----------------------------------------------------------------------------------
+// header parse
+__device__ __forceinline__ uint32_t hdr_byte_at_bit(const uint8_t *sm, uint32_t bit)
+{   // 8 bits starting at bit offset `bit` of the staged bytes
+    uint32_t i = bit >> 3, sh = bit & 7;
+    return ((((uint32_t)sm[i] << 8) | sm[i + 1]) >> (8 - sh)) & 0xFFu;
+}
+
+constexpr uint32_t HDR_STAGE = 64 * 1024;               // staged header bytes
+constexpr uint32_t HDR_MARGIN = 32 * 280 / 8 + 64;      // a full speculative step must fit: 32 entries of <= 24+255 bits
+
+__global__ void __launch_bounds__(1024, 1)
+dec_parse_kernel(const uint8_t *__restrict__ file, unsigned long long file_bytes, TabSrc *__restrict__ src,
+                 DecodeTable *__restrict__ tab, hf_header_info_t *__restrict__ info)
+{
+    extern __shared__ uint8_t sm[];
+    __shared__ unsigned long long s_pos;                // bit position (from the stream start) of the next entry
+    __shared__ uint32_t s_k, s_done, s_err;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    uint32_t U = 0, is_odd = 0, last = 0, pre = 3;
+    bool ok = file_bytes >= 3;
+    if (ok) {
+        U = (uint32_t)file[0] | ((uint32_t)file[1] << 8);           // D:69
+        is_odd = file[2] != 0;                                      // D:76
+        pre = 3 + is_odd;
+        ok = file_bytes >= pre;
+        if (ok && is_odd) last = file[3];                           // D:77-80
+        if (ok && U == 0) U = (file_bytes - pre == 8) ? 0u : 65536u;   // D:70-71; U = 0 is our N < 2 case
+    }
+    const unsigned long long stream_bytes = ok ? file_bytes - pre : 0;
+    const uint8_t *stream = file + pre;
+    if (tid == 0) { s_pos = 0; s_k = 0; s_done = (U == 0 || !ok); s_err = !ok; }
+    __syncthreads();
+
+    while (!s_done) {
+        // stage HDR_STAGE bytes starting at the byte holding s_pos
+        const unsigned long long b0 = s_pos >> 3;
+        for (uint32_t i = tid; i < HDR_STAGE + 16; i += 1024)
+            sm[i] = (b0 + i < stream_bytes) ? stream[b0 + i] : 0;
+        __syncthreads();
+        if (tid < 32) {
+            unsigned long long pos = s_pos;
+            uint32_t k = s_k;
+            uint32_t stride = 0;
+            bool err = false;
+            while (k < U) {
+                uint32_t rel = (uint32_t)(pos - b0 * 8);
+                if ((rel >> 3) + HDR_MARGIN > HDR_STAGE) break;       // restage
+                if ((pos >> 3) + 3 > stream_bytes) { err = true; break; }
+                if (stride == 0) stride = 24 + hdr_byte_at_bit(sm, rel + 16);
+                uint32_t myrel = rel + lane * stride;
+                uint32_t L = hdr_byte_at_bit(sm, myrel + 16);
+                uint32_t mism = __ballot_sync(0xFFFFFFFFu, 24 + L != stride);
+                uint32_t f = mism ? (uint32_t)__ffs(mism) - 1 : 32u;  // entries 0..f sit at their predicted places
+                uint32_t n_ok = min(f + 1, 32u);
+                n_ok = min(n_ok, U - k);
+                if (lane < n_ok) {
+                    src->entry_pos[k + lane] = pos + (unsigned long long)lane * stride;
+                    src->len[k + lane] = L;
+                }
+                // advance past the confirmed entries
+                uint32_t Lf = __shfl_sync(0xFFFFFFFFu, L, n_ok - 1);
+                pos += (unsigned long long)(n_ok - 1) * stride + 24 + Lf;
+                k += n_ok;
+                stride = 24 + Lf;
+            }
+            if (lane == 0) {
+                s_pos = pos; s_k = k;
+                if (err) { s_err = 1; s_done = 1; }
+                if (k >= U) s_done = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        unsigned long long pos = s_pos;
+        unsigned long long n = 0;
+        bool err = s_err;
+        if (!err && (pos + 64 + 7) / 8 > stream_bytes) err = true;
+        if (!err) {
+            for (int i = 0; i < 8; i++) {                              // D:243-255
+                unsigned long long bit = pos + 8 * i;
+                uint32_t bi = (uint32_t)(bit & 7);
+                uint32_t v = ((((uint32_t)stream[bit >> 3] << 8) |
+                               ((bit >> 3) + 1 < stream_bytes ? stream[(bit >> 3) + 1] : 0u)) >> (8 - bi)) & 0xFFu;
+                n |= (unsigned long long)v << (8 * i);
+            }
+            if ((n & 1) != is_odd) err = true;
+        }
+        src->U = err ? 0 : U;
+        info->n_unique = U; info->is_odd = is_odd; info->last_byte = last;
+        info->original_bytes = n;
+        info->payload_start_bit = pre * 8ull + pos + 64;
+        info->status = err ? HF_ERR_FORMAT : HF_OK;
+        info->max_code_bits = 0;
+        if (err) tab->status = HF_ERR_FORMAT;
+    }
+}
+
+// up to 64 bits at an arbitrary bit position of a byte buffer, zero past the end
+__device__ __forceinline__ unsigned long long bits_at(const uint8_t *p, unsigned long long nbytes,
+                                                      unsigned long long bitpos, uint32_t nbits)
+{
+    unsigned long long v = 0;
+    unsigned long long b = bitpos >> 3;
+    uint32_t sh = (uint32_t)(bitpos & 7), got = 0;
+    // first (partial) byte, then whole bytes
+    while (got < nbits) {
+        uint32_t byte = b < nbytes ? p[b] : 0u;
+        uint32_t avail = 8 - sh;
+        uint32_t take = min(avail, nbits - got);
+        uint32_t chunk = (byte >> (avail - take)) & ((1u << take) - 1);
+        v = (v << take) | chunk;
+        got += take; sh = 0; b++;
+    }
+    return v;
+}
+
+// pulls (sym, code) of every entry out of the file image once the entry positions are known
+__global__ void dec_entries_kernel(const uint8_t *__restrict__ file, unsigned long long file_bytes,
+                                   TabSrc *__restrict__ src)
+{
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= src->U) return;
+    const uint32_t pre = 3 + (file[2] != 0);
+    const uint8_t *stream = file + pre;
+    const unsigned long long nb = file_bytes - pre;
+    const unsigned long long pos = src->entry_pos[k];
+    uint32_t sym = (uint32_t)bits_at(stream, nb, pos, 16);           // D:178-182
+    uint32_t len = (uint32_t)bits_at(stream, nb, pos + 16, 8);       // D:93
+    unsigned long long code = 0;
+    if (len && len <= 64) code = bits_at(stream, nb, pos + 24, len); // D:129-163
+    src->sym[k] = sym;
+    src->len[k] = len;
+    src->code[k] = code;
+}
+
+// -----------------------------------------------------------------------------------
+// chunk staging: frame words [c * CHUNK_WORDS, + CHUNK_WORDS + pad) as big-endian words
+__device__ __forceinline__ void stage_chunk(uint32_t *sw, const uint8_t *frame, unsigned long long frame_bytes,
+                                            unsigned long long chunk)
+{
+    const unsigned long long v0 = chunk * (CHUNK_WORDS / 4);
+    for (uint32_t i = threadIdx.x; i < (CHUNK_WORDS + CHUNK_PAD_WORDS) / 4; i += DEC_THREADS) {
+        unsigned long long byte = (v0 + i) * 16ull;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (byte < frame_bytes) v = ld_stream_v4(frame + byte);      // same 16-byte block as a valid byte
+        v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
+        reinterpret_cast<uint4 *>(sw)[i] = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t spec_start(unsigned long long X, unsigned long long F0, uint32_t g)
+{   // first offset >= 0 from frame bit X at which a code word can start (boundaries are F0 + k*g)
+    if (g <= 1) return 0;
+    uint32_t r = (uint32_t)((X - F0) % g);
+    return r ? g - r : 0;
+}
+
+// full decode of one subsequence from offset p: overflow, count and the boundary mask of the first 64 bits
+template <typename F>
+__device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t sub_bit0, uint32_t p,
+                                                 uint32_t &end, uint32_t &cnt_hi, unsigned long long &mask,
+                                                 uint32_t &bad)
+{
+    BitReader<F> r{f};
+    r.init(sub_bit0 + p);
+    uint32_t pos = p;
+    mask = 0; cnt_hi = 0;
+    while (pos < 64) {
+        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
+        mask |= 1ull << pos;
+        pos += len;
+        r.skip(len);
+    }
+    while (pos < SUB_BITS) {
+        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
+        cnt_hi++;
+        pos += len;
+        r.skip(len);
+    }
+    end = pos - SUB_BITS;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS)
+dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+                const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch)
+{
+    __shared__ __align__(16) uint32_t sw[CHUNK_WORDS + CHUNK_PAD_WORDS];
+    __shared__ uint32_t st1[1u << K1];
+    __shared__ uint32_t s_end[DEC_THREADS];
+    if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
+    DecLayout L(work, nch);
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long c = blockIdx.x;
+    for (uint32_t i = tid; i < (1u << K1); i += DEC_THREADS) st1[i] = tab->t1[i];
+    stage_chunk(sw, frame, frame_bytes, c);
+    __syncthreads();
+
+    TabView T{st1, tab->t2, tab->longs, tab->n_long};
+    SmemFetch f{sw};
+    const uint32_t g = tab->len_gcd;
+    const uint32_t sub_bit0 = tid * SUB_BITS;
+    const unsigned long long X = c * CHUNK_BITS + sub_bit0;
+    const bool fixed = (c == 0 && tid == 0);            // holds the first payload bit: exact start
+    uint32_t p = fixed ? (uint32_t)F0 : spec_start(X, F0, g);
+    uint32_t end, cnt_hi, bad = 0;
+    unsigned long long mask;
+    sub_decode_count(T, f, sub_bit0, p, end, cnt_hi, mask, bad);
+    uint32_t cnt = __popcll(mask) + cnt_hi;
+
+    for (uint32_t it = 0; it < DEC_THREADS + 1; it++) {
+        s_end[tid] = end;
+        __syncthreads();
+        int changed = 0;
+        if (tid > 0 && !fixed) {
+            uint32_t q = s_end[tid - 1];
+            if (q != p) {
+                // re-synchronise: decode from q until a boundary the recorded walk also visited
+                BitReader<SmemFetch> r{f};
+                r.init(sub_bit0 + q);
+                uint32_t pos = q, k = 0;
+                unsigned long long nmask = 0;
+                bool hit = false;
+                while (pos < 64) {
+                    if ((mask >> pos) & 1ull) { hit = true; break; }
+                    uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
+                    nmask |= 1ull << pos;
+                    pos += len; k++;
+                    r.skip(len);
+                }
+                if (hit) {
+                    cnt = k + __popcll(mask >> pos) + cnt_hi;
+                    mask = nmask | ((mask >> pos) << pos);
+                } else {
+                    uint32_t nhi = 0;
+                    while (pos < SUB_BITS) {
+                        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
+                        nhi++;
+                        pos += len;
+                        r.skip(len);
+                    }
+                    uint32_t nend = pos - SUB_BITS;
+                    changed = nend != end;
+                    end = nend; mask = nmask; cnt_hi = nhi; cnt = k + nhi;
+                }
+                p = q;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    L.info[c * DEC_THREADS + tid] = (uint16_t)((p & 63u) | (cnt << 6));
+    // chunk totals
+    uint32_t v = cnt;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) s_end[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int i = 0; i < DEC_THREADS / 32; i++) tot += s_end[i];
+        L.chunkCnt[c] = tot;
+        L.chunkE2[c] = 0xFFFFFFFFu;
+    }
+    if (tid == DEC_THREADS - 1) L.chunkE[c] = end;
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// repairs chunk c from the true start `s` (frame offset inside the chunk's subsequence 0).
+// Returns true when the walk re-joined the recorded chain before the chunk ended.
+__device__ bool fix_chunk(const TabView &T, const uint8_t *frame, unsigned long long frame_bytes,
+                          DecLayout &L, unsigned long long c, uint32_t s, uint32_t &bad)
+{
+    uint16_t *info = L.info + c * DEC_THREADS;
+    GlobalFetch f{frame, frame_bytes, c * CHUNK_WORDS};
+    uint32_t q = s;
+    long long delta = 0;
+    for (uint32_t t = 0; t < DEC_THREADS; t++) {
+        uint32_t end, cnt_hi;
+        unsigned long long mask;
+        sub_decode_count(T, f, t * SUB_BITS, q, end, cnt_hi, mask, bad);
+        uint32_t cnt = __popcll(mask) + cnt_hi;
+        uint32_t old = info[t];
+        delta += (long long)cnt - (long long)(old >> 6);
+        info[t] = (uint16_t)(q | (cnt << 6));
+        if (t + 1 == DEC_THREADS) {
+            L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
+            uint32_t curE = L.chunkE2[c] != 0xFFFFFFFFu ? L.chunkE2[c] : L.chunkE[c];
+            if (end != curE) { L.chunkE2[c] = end; return false; }
+            return true;
+        }
+        if ((uint32_t)(info[t + 1] & 63u) == end) break;
+        q = end;
+    }
+    L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
+    return true;
+}
+
+__global__ void dec_fix_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
+                               const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch)
+{
+    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (c >= nch || tab->single_sym) return;
+    DecLayout L(work, nch);
+    uint32_t s = L.chunkE[c - 1];
+    if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
+    TabView T{tab->t1, tab->t2, tab->longs, tab->n_long};
+    uint32_t bad = 0;
+    if (!fix_chunk(T, frame, frame_bytes, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// streams that do not synchronise within a whole chunk: carry the true start forward serially
+__global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
+                                      const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch)
+{
+    if (work->flags[0] == 0 || tab->single_sym) return;
+    DecLayout L(work, nch);
+    TabView T{tab->t1, tab->t2, tab->longs, tab->n_long};
+    uint32_t bad = 0;
+    for (unsigned long long c = 1; c < nch; c++) {
+        if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix_kernel used
+        uint32_t s = L.chunkE2[c - 1];
+        if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
+        fix_chunk(T, frame, frame_bytes, L, c, s, bad);
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+dec_scan_kernel(DecWork *work, unsigned long long nch)
+{
+    __shared__ unsigned long long s_w[33];
+    DecLayout L(work, nch);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long per = (nch + 1023) / 1024;
+    const unsigned long long lo = min(nch, tid * per), hi = min(nch, (tid + 1) * per);
+    unsigned long long sum = 0;
+    for (unsigned long long i = lo; i < hi; i++) sum += L.chunkCnt[i];
+    unsigned long long x = sum;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = s_w[lane], t = s;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        s_w[lane] = t - s;
+    }
+    __syncthreads();
+    unsigned long long run = x - sum + s_w[wid];
+    for (unsigned long long i = lo; i < hi; i++) { L.chunkBase[i] = run; run += L.chunkCnt[i]; }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS)
+dec_write_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+                 const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
+                 unsigned long long n_symbols, uint16_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint32_t dyn_smem[];
+    uint32_t *sw = dyn_smem;                                        // CHUNK_WORDS + CHUNK_PAD_WORDS
+    uint32_t *st1 = sw + CHUNK_WORDS + CHUNK_PAD_WORDS;             // 2^K1
+    uint16_t *sout = reinterpret_cast<uint16_t *>(st1 + (1u << K1)); // WIN_SYMS + 8
+    __shared__ uint32_t s_w[33];
+    if (tab->single_sym) return;
+    DecLayout L(work, nch);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long c = blockIdx.x;
+    const unsigned long long base = L.chunkBase[c];
+    if (base >= n_symbols) return;
+    for (uint32_t i = tid; i < (1u << K1); i += DEC_THREADS) st1[i] = tab->t1[i];
+    stage_chunk(sw, frame, frame_bytes, c);
+
+    const uint32_t inf = L.info[c * DEC_THREADS + tid];
+    const uint32_t p = (c == 0 && tid == 0) ? (uint32_t)F0 : (inf & 63u);   // the stream head may sit past bit 63
+    uint32_t remaining = inf >> 6;
+    // exclusive scan of the counts inside the chunk
+    uint32_t x = remaining;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < DEC_THREADS / 32 ? s_w[lane] : 0u, t = s;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        if (lane < DEC_THREADS / 32) s_w[lane] = t - s;
+        if (lane == 31) s_w[32] = t;
+    }
+    __syncthreads();
+    uint32_t next = x - remaining + s_w[wid];           // chunk-relative index of my next symbol
+    unsigned long long total = s_w[32];
+    if (base + total > n_symbols) total = n_symbols - base;   // garbage past the payload end is dropped
+
+    TabView T{st1, tab->t2, tab->longs, tab->n_long};
+    SmemFetch f{sw};
+    BitReader<SmemFetch> r{f};
+    const uint32_t sub_bit0 = tid * SUB_BITS;
+    r.init(sub_bit0 + p);
+    uint32_t pos = p, bad = 0;
+
+    const uint32_t mis = (uint32_t)(base & 7);          // staging slot j <-> output symbol base - mis + j
+    for (unsigned long long w0 = 0; w0 < total; w0 += WIN_SYMS) {
+        const unsigned long long wend = min(total, w0 + WIN_SYMS);
+        while (remaining && next < wend) {
+            uint32_t e = decode_one(T, r, sub_bit0 + pos, bad);
+            uint32_t len = e & 0x7Fu;
+            sout[next - (uint32_t)w0 + mis] = (uint16_t)(e >> 8);
+            pos += len;
+            r.skip(len);
+            next++; remaining--;
+        }
+        if (remaining && next >= total) remaining = 0;
+        __syncthreads();
+        // flush [w0, wend): staging slots [mis, mis + n)
+        const uint32_t n = (uint32_t)(wend - w0);
+        uint16_t *dst = out + base + w0 - mis;          // 16-byte aligned when out is
+        const uint32_t nvec = (mis + n + 7) / 8;
+        for (uint32_t q = tid; q < nvec; q += DEC_THREADS) {
+            const uint32_t j0 = q * 8;
+            if (j0 >= mis && j0 + 8 <= mis + n && (((uintptr_t)(dst + j0) & 15) == 0)) {
+                st_stream_v4(dst + j0, reinterpret_cast<const uint4 *>(sout)[q]);
+            } else {
+                for (uint32_t j = j0; j < j0 + 8; j++)
+                    if (j >= mis && j < mis + n) dst[j] = sout[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// U == 1 with a zero-length code: the payload is empty, every symbol is the same
+__global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned long long n_symbols,
+                                uint16_t *__restrict__ out)
+{
+    if (!(tab->single_sym & 0x10000u)) return;
+    const uint16_t s = (uint16_t)tab->single_sym;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n_symbols; i += stride) out[i] = s;
+}
+
+// -----------------------------------------------------------------------------------
+static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
+{
+    // zero everything but the (large) long list; t2 zero = invalid
+    HF_CUDA(c, cudaMemsetAsync(d_tab, 0, offsetof(DecodeTable, longs), c->stream));
+    HF_CUDA(c, cudaMemsetAsync(src->len_mask, 0, sizeof(src->len_mask), c->stream));
+    dt_depth_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab, src->len_mask);
+    HF_LAUNCH_CHECK(c);
+    dt_offsets_kernel<<<1, 1024, 0, c->stream>>>(src, d_tab, src->len_mask);
+    HF_LAUNCH_CHECK(c);
+    dt_fill_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab)
+{
+    int rc = ensure_ws(c, sizeof(TabSrc));
+    if (rc) return rc;
+    TabSrc *src = reinterpret_cast<TabSrc *>(c->ws);
+    dt_from_codebook_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, src);
+    HF_LAUNCH_CHECK(c);
+    return build_tables(c, src, d_tab);
+}
+
+int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, DecodeTable *d_tab,
+                        hf_header_info_t *d_info)
+{
+    int rc = ensure_ws(c, sizeof(TabSrc));
+    if (rc) return rc;
+    TabSrc *src = reinterpret_cast<TabSrc *>(c->ws);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HF_CUDA(c, cudaFuncSetAttribute(dec_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HDR_STAGE + 32));
+        attr_set = true;
+    }
+    // status of an earlier use must not leak into this parse
+    HF_CUDA(c, cudaMemsetAsync(&d_tab->status, 0, sizeof(uint32_t), c->stream));
+    dec_parse_kernel<<<1, 1024, HDR_STAGE + 32, c->stream>>>(d_file, file_bytes, src, d_tab, d_info);
+    HF_LAUNCH_CHECK(c);
+    dec_entries_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_file, file_bytes, src);
+    HF_LAUNCH_CHECK(c);
+    return build_tables(c, src, d_tab);
+}
+
+int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
+                  uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out)
+{
+    if (n_symbols == 0) return HF_OK;
+    if ((uintptr_t)d_out & 1) return set_err(c, HF_ERR_ARG, "hf_decode: output must be 2-byte aligned");
+    if ((start_bit >> 3) > stream_bytes) return set_err(c, HF_ERR_ARG, "hf_decode: start bit past the stream");
+    d_stream += start_bit >> 3;
+    stream_bytes -= start_bit >> 3;
+    start_bit &= 7;
+    const uint8_t *frame = reinterpret_cast<const uint8_t *>((uintptr_t)d_stream & ~(uintptr_t)15);
+    const unsigned long long lead = (uintptr_t)d_stream & 15;
+    const unsigned long long frame_bytes = lead + stream_bytes;
+    const unsigned long long F0 = lead * 8 + start_bit;
+    unsigned long long nch = (frame_bytes * 8 + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (nch == 0) nch = 1;                              // zero-length codes: nothing to read
+    if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
+
+    const size_t off = 8u << 20;                        // behind the table-source / codebook workspace
+    int rc = ensure_ws(c, off + DecLayout::bytes(nch));
+    if (rc) return rc;
+    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
+    HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
+
+    uint16_t *out16 = reinterpret_cast<uint16_t *>(d_out);
+    dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, out16);
+    HF_LAUNCH_CHECK(c);
+    dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch);
+    HF_LAUNCH_CHECK(c);
+    if (nch > 1) {
+        dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
+        HF_LAUNCH_CHECK(c);
+        dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
+        HF_LAUNCH_CHECK(c);
+    }
+    dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch);
+    HF_LAUNCH_CHECK(c);
+    const size_t wsmem = (CHUNK_WORDS + CHUNK_PAD_WORDS + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
+    static bool wattr = false;
+    if (!wattr) {
+        HF_CUDA(c, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        wattr = true;
+    }
+    dec_write_kernel<<<(unsigned)nch, DEC_THREADS, wsmem, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+}  // namespace hf

@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path behind the C ABI against the CPU oracle (bit-exact: all of
+this is integer / byte work), on seeded inputs and on the committed fixtures, plus
+size-independent properties at BASELINE.json's full sizes.  Run with `pytest -m gpu`.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from cases import fibonacci_hist, small_cases
+from conftest import GOLDEN, ROOT
+from huffman_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = small_cases()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---------------------------------------------------------------- histogram (row a1)
+@pytest.mark.parametrize("name", list(CASES))
+def test_histogram_matches_oracle(codec, oracle, name):
+    data = CASES[name]
+    want = oracle.histogram(data)
+    got = codec.histogram(dev(data)) if data.size else torch.zeros(65536, dtype=torch.int64, device="cuda")
+    assert np.array_equal(got.cpu().numpy().astype(np.uint64), want)
+
+
+def test_histogram_large_and_unaligned(codec, oracle):
+    data = synth.zipf1g(8 << 20)
+    d = dev(data)
+    for off, n in ((0, data.size), (2, data.size - 2), (14, (4 << 20) + 6), (16, 1 << 20)):
+        got = codec.histogram(d[off:off + n])
+        assert np.array_equal(got.cpu().numpy().astype(np.uint64), oracle.histogram(data[off:off + n])), (off, n)
+    # accumulation across shards == histogram of the whole (linearity)
+    acc = codec.histogram(d[: 3 << 20])
+    codec.histogram(d[3 << 20:], acc)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), oracle.histogram(data))
+
+
+def test_histogram_hot_bin_spills(codec, oracle):
+    # one bin far beyond 16 bits per CTA: exercises the 0x8000 spill path
+    data = np.zeros(64 << 20, np.uint8)
+    data[1::4096] = 7
+    got = codec.histogram(dev(data))
+    assert np.array_equal(got.cpu().numpy().astype(np.uint64), oracle.histogram(data))
+
+
+# ---------------------------------------------------------------- codebook (rows a2-a5)
+def check_codebook(codec, oracle, hist_np):
+    cb = codec.build_codebook(dev(hist_np.astype(np.int64)))
+    info = cb.info()
+    ocb = oracle.codebook(hist_np)
+    o_order, o_len, o_code = ocb.arrays()
+    order, ln, code = cb.export()
+    assert info.status == 0
+    assert info.n_unique == ocb.U
+    assert np.array_equal(order[: ocb.U], o_order[: ocb.U])
+    assert np.array_equal(ln, o_len)
+    assert np.array_equal(code, o_code)
+    assert info.max_code_bits == ocb.maxlen
+    assert info.table_bits == ocb.table_bits
+    assert info.payload_bits == ocb.payload_bits
+    return cb, ocb
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_codebook_matches_oracle(codec, oracle, name):
+    check_codebook(codec, oracle, oracle.histogram(CASES[name]))
+
+
+def test_codebook_fixtures(codec, oracle, romeo, jpeg):
+    _, o1 = check_codebook(codec, oracle, oracle.histogram(romeo))
+    assert (o1.U, o1.maxlen) == (1268, 16)
+    _, o2 = check_codebook(codec, oracle, oracle.histogram(jpeg))
+    assert (o2.U, o2.maxlen) == (65289, 21)
+
+
+def test_codebook_fuzz_ties(codec, oracle):
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        U = int(rng.integers(2, 3000))
+        h = np.zeros(65536, np.uint64)
+        syms = rng.choice(65536, U, replace=False)
+        kind = trial % 4
+        if kind == 0:
+            h[syms] = rng.integers(1, 4, U)                     # tie-heavy
+        elif kind == 1:
+            h[syms] = 1 << rng.integers(0, 12, U)               # powers of two
+        elif kind == 2:
+            h[syms] = rng.integers(1, 1 << 40, U)               # > 32-bit counts
+        else:
+            h[syms] = np.maximum(1, (rng.pareto(1.1, U) * 10).astype(np.uint64))
+        check_codebook(codec, oracle, h)
+
+
+def test_codebook_long_codes(codec, oracle):
+    for n in (30, 45, 60):
+        _, ocb = check_codebook(codec, oracle, fibonacci_hist(n))
+        assert ocb.maxlen == n - 1
+
+
+def test_codebook_too_long_is_reported(codec):
+    h = np.zeros(65536, np.uint64)
+    a, b = 1, 1
+    for i in range(70):                                          # depth 69 > 64
+        h[i] = a
+        a, b = b, a + b
+    cb = codec.build_codebook(dev(h.astype(np.int64)))
+    assert cb.info().status == 5                                 # HF_ERR_CODE_TOO_LONG
+
+
+# ---------------------------------------------------------------- compress (rows a6-a9)
+@pytest.mark.parametrize("name", list(CASES))
+def test_compress_byte_identical_to_oracle(codec, oracle, name):
+    data = CASES[name]
+    want = oracle.compress(data)
+    got = codec.compress(dev(data) if data.size else torch.zeros(0, dtype=torch.uint8, device="cuda"))
+    got = got.cpu().numpy()
+    assert got.size == want.size
+    assert np.array_equal(got, want), f"first diff at byte {np.flatnonzero(got != want)[:4]}"
+
+
+def test_compress_fixtures_golden(codec, oracle, romeo, jpeg):
+    gold = json.load(open(os.path.join(GOLDEN, "reference_hashes.json")))
+    for name, data in (("romeo.txt", romeo), ("pexels.jpg", jpeg)):
+        got = codec.compress(dev(data)).cpu().numpy()
+        assert np.array_equal(got, oracle.compress(data))
+        assert got.size == gold[name]["compressed_bytes"]
+        assert sha(got) == gold[name]["compressed_sha256"]
+
+
+def test_compress_pdf_standin_and_unaligned_output(codec, oracle):
+    data = synth.pdf15m()
+    want = oracle.compress(data)
+    d = dev(data)
+    assert np.array_equal(codec.compress(d).cpu().numpy(), want)
+    # any alignment of the output image must give the same bytes
+    buf = torch.empty(codec.compress_bound(data.size) + 64, dtype=torch.uint8, device="cuda")
+    for off in (1, 5, 13, 16):
+        got = codec.compress(d, buf[off:])
+        assert np.array_equal(got.cpu().numpy(), want), off
+
+
+def test_encode_long_codes(codec, oracle):
+    # Fibonacci counts give code lengths up to 44: the 64-bit encoder variant and the long-code
+    # decode list.  Data: every symbol of the alphabet a few times, rare ones included.
+    h = fibonacci_hist(45)
+    syms = np.flatnonzero(h).astype(np.uint16)
+    rng = np.random.default_rng(3)
+    data = np.concatenate([syms, rng.choice(syms, 200000), syms[::-1]]).astype(np.uint16).view(np.uint8)
+    cb = codec.build_codebook(dev(h.astype(np.int64)))
+    ocb = oracle.codebook(h)
+    _, o_len, o_code = ocb.arrays()
+    # expected stream from the oracle's code table
+    bits = []
+    for s in data.view(np.uint16):
+        bits.append(format(int(o_code[s]), "b").zfill(int(o_len[s])) if o_len[s] else "")
+    bitstr = "".join(bits)
+    for start_bit in (0, 3, 7):
+        want = np.packbits(np.frombuffer(("0" * start_bit + bitstr).encode(), np.uint8) - ord("0"))
+        out = torch.zeros(want.size + 32, dtype=torch.uint8, device="cuda")
+        codec.encode(dev(data), cb, out, start_bit)
+        got = out.cpu().numpy()[: want.size]
+        assert np.array_equal(got, want), start_bit
+        # and back through the decoder
+        table = codec.decode_table_from_codebook(cb)
+        dec = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+        codec.decode(out, start_bit, data.size // 2, table, dec)
+        codec.sync()
+        assert np.array_equal(dec.cpu().numpy(), data)
+
+
+# ---------------------------------------------------------------- decompress (rows a10-a11)
+@pytest.mark.parametrize("name", list(CASES))
+def test_decompress_oracle_images(codec, oracle, name):
+    data = CASES[name]
+    image = oracle.compress(data)
+    got = codec.decompress(dev(image))
+    assert np.array_equal(got.cpu().numpy(), data)
+
+
+def test_round_trip_fixtures(codec, romeo, jpeg):
+    for data in (romeo, jpeg, synth.pdf15m()):
+        d = dev(data)
+        assert torch.equal(codec.decompress(codec.compress(d)), d)
+
+
+def test_decompress_baseline_cpu_images(codec, oracle, romeo):
+    """files written by the reference's baseline/ CPU compressor (different tie-breaking) decode too"""
+    exe = oracle.ref_binary("cpu_archive")
+    if exe is None:
+        pytest.skip("oracle/_ref/cpu_archive not built")
+    with tempfile.TemporaryDirectory() as td:
+        for name, data in (("romeo", romeo), ("zipf", synth.zipf_bytes(300001, 1.2, 3))):
+            p = os.path.join(td, name)
+            data.tofile(p)
+            subprocess.run([exe, p], cwd=td, check=True, stdout=subprocess.DEVNULL)
+            image = np.fromfile(p + ".compressed", dtype=np.uint8)
+            assert np.array_equal(codec.decompress(dev(image)).cpu().numpy(), data)
+
+
+def test_reference_extract_decodes_our_images(codec, oracle, romeo):
+    exe = oracle.ref_binary("ref_extract")
+    if exe is None:
+        pytest.skip("oracle/_ref/ref_extract not built")
+    with tempfile.TemporaryDirectory() as td:
+        for name, data in (("romeo", romeo), ("zipf", synth.zipf_bytes(300001, 1.2, 3))):
+            p = os.path.join(td, name + ".compressed")
+            codec.compress(dev(data)).cpu().numpy().tofile(p)
+            subprocess.run([exe, p], cwd=td, check=True, stdout=subprocess.DEVNULL)
+            out = os.path.join(td, "DECOMPRESSED_FILE")
+            assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
+            os.remove(out)
+
+
+def test_malformed_images_are_rejected(codec, oracle, romeo):
+    from huffman_b200 import HuffmanError
+    image = oracle.compress(romeo)
+    with pytest.raises(HuffmanError):
+        codec.decompress(dev(image[:9]))
+    bad = image.copy()
+    bad[6] = 0                                                    # first entry: a zero code length with U > 1
+    with pytest.raises(HuffmanError):
+        codec.decompress(dev(bad))
+
+
+# ---------------------------------------------------------------- host-buffer calls and the programs (row b)
+def test_host_calls_match_device_calls(codec, oracle):
+    data = synth.zipf1g((5 << 20) + 3)
+    want = oracle.compress(data)
+    h_in = torch.from_numpy(data).pin_memory()
+    image = codec.compress_host(h_in)
+    assert np.array_equal(image.numpy(), want)
+    back = codec.decompress_host(image)
+    assert np.array_equal(back.numpy(), data)
+    # pageable memory works too
+    image2 = codec.compress_host(torch.from_numpy(data.copy()), torch.empty(codec.compress_bound(data.size), dtype=torch.uint8))
+    assert np.array_equal(image2.numpy(), want)
+
+
+def test_archive_extract_programs(oracle, romeo):
+    """bin/archive and bin/extract keep the reference's command line and file names (Makefile:17-29)"""
+    archive, extract = os.path.join(ROOT, "bin", "archive"), os.path.join(ROOT, "bin", "extract")
+    assert os.path.exists(archive) and os.path.exists(extract), "build() did not produce the programs"
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "romeo.txt")
+        romeo.tofile(p)
+        r = subprocess.run([archive, p], cwd=td, capture_output=True, text=True, check=True)
+        assert "Unique symbols count: 1268" in r.stdout and "Compression is complete" in r.stdout
+        image = np.fromfile(p + ".compressed", dtype=np.uint8)
+        assert np.array_equal(image, oracle.compress(romeo))
+        for expect in ("DECOMPRESSED_FILE", "DECOMPRESSED_FILE(1)", "DECOMPRESSED_FILE(2)"):
+            r = subprocess.run([extract, p + ".compressed"], cwd=td, capture_output=True, text=True, check=True)
+            assert "Decompression is complete" in r.stdout
+            assert np.array_equal(np.fromfile(os.path.join(td, expect), dtype=np.uint8), romeo)
+        assert subprocess.run([archive], cwd=td, capture_output=True).returncode == 0      # C:317-321
+        assert subprocess.run([extract], cwd=td, capture_output=True).returncode == 1      # D:51-56
+
+
+# ---------------------------------------------------------------- full-size properties (configs 4 and 5)
+def test_zipf1g_properties(codec, oracle):
+    n = 1 << 30
+    d = synth.zipf1g(n, device="cuda")
+    hist = codec.histogram(d)
+    assert int(hist.sum()) == n // 2
+    # the first 4 MiB agree with the oracle (same generator on the host)
+    head = synth.zipf1g(n, count=4 << 20)
+    assert np.array_equal(d[: 4 << 20].cpu().numpy(), head)
+    image = codec.compress(d)
+    cb = codec.build_codebook(hist)
+    info = cb.info()
+    assert image.numel() == 3 + (info.table_bits + 64 + info.payload_bits + 7) // 8
+    # shard linearity: dot(shard hist, len) sums to the payload size
+    parts = [codec.shard_payload_bits(codec.histogram(d[i * (n // 4):(i + 1) * (n // 4)]), cb) for i in range(4)]
+    assert sum(int(p.item()) for p in parts) == info.payload_bits
+    back = codec.decompress(image)
+    assert back.numel() == n and torch.equal(back, d)
+    # a prefix that the oracle finishes in seconds is byte-identical
+    m = 32 << 20
+    assert np.array_equal(codec.compress(d[:m]).cpu().numpy(), oracle.compress(d[:m].cpu().numpy()))
+
+
+def test_mixed_entropy_round_trip(codec):
+    n = 3 << 30                                                   # > 2^31 bytes: beyond the reference's int indices (R3)
+    d = synth.mixed(n, seg_bytes=1 << 29, device="cuda")
+    image = codec.compress(d)
+    back = codec.decompress(image)
+    assert back.numel() == n and torch.equal(back, d)
