@@ -89,11 +89,8 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     if (!c) return HF_ERR_ARG;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
-    else {
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { free(c); return HF_ERR_CUDA; }
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)stream;                   // NULL = the legacy default stream, as the reference uses
+    c->own_stream = false;
     bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scratch, 4096) == cudaSuccess;

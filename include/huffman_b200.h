@@ -68,8 +68,8 @@ typedef struct {
 
 /* ---- lifecycle -------------------------------------------------------- */
 
-/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on (e.g. torch's
- * current stream), or NULL to let the context create its own. */
+/* device: CUDA ordinal.  stream: the cudaStream_t to enqueue on (e.g. torch's current
+ * stream); NULL is the legacy default stream, which is what the reference runs on. */
 int hf_ctx_create(hf_ctx **ctx, int device, void *stream);
 int hf_ctx_destroy(hf_ctx *ctx);
 int hf_ctx_set_stream(hf_ctx *ctx, void *stream);
