@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py — encode / decode throughput of the Huffman hot path on 1..8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (the reference's own CPU path, host cores)
+
+A STEP is one pass of the hot path over the workload: the whole stream is compressed
+(histogram -> [all-reduce] -> codebook -> header -> single-pass encode) and then decompressed
+(header parse -> tables -> self-synchronising decode), sharded by contiguous chunk over the N ranks.
+`value` = uncompressed bytes coded per second (N bytes through compress + N bytes through
+decompress per step), inputs resident in HBM; `encode_gbs` / `decode_gbs` give the two halves.
+Total work is fixed as N grows (BASELINE.json configs 4/5 are one stream at 1/2/4/8 GPUs): strong scaling.
+
+Timing: W >= 3 warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events on the
+launching stream, max over ranks.  The workload (>= 1 GiB in, same out) is far larger than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "encode+decode throughput (uncompressed GB/s), byte-identical to the reference format"
+UNIT = "GB/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ workload
+def workload_bytes(name, override):
+    if override:
+        return int(override)
+    return {"mixed16g": 16 << 30, "zipf1g": 1 << 30}[name]
+
+
+def make_chunk(name, n_total, lo, hi, device):
+    """bytes [lo, hi) of the named synthetic stream, generated on `device` (counter-based: any shard alone)"""
+    from huffman_b200 import synth
+    if name == "zipf1g":
+        return synth.zipf1g(n_total, start=lo, count=hi - lo, device=device)
+    seg = max(1 << 20, n_total // 16)          # BASELINE config 5: 16 segments cycling six entropy classes
+    return synth.mixed(n_total, seg_bytes=seg, device=device, start=lo, count=hi - lo)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """samples SM clock and throttle reasons during the timed region (pynvml; nvidia-smi as fallback)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        names = {
+            pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                self.samples.append(int(f[0]))
+                self.max_mhz = int(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        def run():
+            try:
+                self._run_nvml()
+            except Exception:
+                self._run_smi()
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU baseline (the reference's own CPU path)
+def cpu_reference_step(sample, workdir):
+    """one archive + extract of `sample` (numpy uint8) with the UNMODIFIED reference baseline/ programs
+    (oracle/_ref/cpu_archive, cpu_extract: single-threaded by construction); falls back to the oracle port.
+    Returns (seconds_compress, seconds_decompress, kind, cores)."""
+    from oracle import oracle as O
+    arch, extr = O.ref_binary("cpu_archive"), O.ref_binary("cpu_extract")
+    if arch and extr:
+        p = os.path.join(workdir, "sample.bin")
+        sample.tofile(p)
+        for f in ("DECOMPRESSED_FILE",):
+            if os.path.exists(os.path.join(workdir, f)):
+                os.remove(os.path.join(workdir, f))
+        t0 = time.perf_counter()
+        subprocess.run([arch, p], cwd=workdir, check=True, stdout=subprocess.DEVNULL)
+        t1 = time.perf_counter()
+        subprocess.run([extr, p + ".compressed"], cwd=workdir, check=True, stdout=subprocess.DEVNULL)
+        t2 = time.perf_counter()
+        back = np.fromfile(os.path.join(workdir, "DECOMPRESSED_FILE"), dtype=np.uint8)
+        assert np.array_equal(back, sample), "reference CPU round trip failed"
+        os.remove(os.path.join(workdir, "DECOMPRESSED_FILE"))
+        return t1 - t0, t2 - t1, "reference", 1
+    t0 = time.perf_counter()
+    img = O.compress(sample)
+    t1 = time.perf_counter()
+    back = O.decompress(img)
+    t2 = time.perf_counter()
+    assert np.array_equal(back, sample)
+    return t1 - t0, t2 - t1, "port", 1
+
+
+def cpu_sample(name, n_total, sample_bytes):
+    """a bounded sample of the workload: equal pieces from the start of every entropy segment"""
+    pieces = 16 if name == "mixed16g" else 1
+    per = max(2, (sample_bytes // pieces) & ~1)
+    seg = n_total // pieces
+    parts = [make_chunk(name, n_total, k * seg, min(n_total, k * seg + per), None) for k in range(pieces)]
+    return np.concatenate(parts) if len(parts) > 1 else parts[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_total = workload_bytes(args.workload, args.bytes)
+    sample = cpu_sample(args.workload, n_total, args.cpu_sample_mb << 20)
+    ts = []
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(args.warmup + args.steps):
+            tc, tdx, kind, cores = cpu_reference_step(sample, td)
+            if i >= args.warmup:
+                ts.append((tc, tdx))
+    tcs, tds = sum(t[0] for t in ts), sum(t[1] for t in ts)
+    k = len(ts)
+    value = 2 * sample.size * k / (tcs + tds) / 1e9
+    desc = f"{sample.size} bytes of {args.workload} (equal pieces from each entropy segment) per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (tcs + tds) / k * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "bytes": n_total, "sample_bytes": int(sample.size)},
+        "encode_gbs": sample.size * k / tcs / 1e9, "decode_gbs": sample.size * k / tds / 1e9,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+                         "host_cores_available": os.cpu_count(),
+                         "note": "baseline/Compressor.cu + baseline/Decompressor.cu are single-threaded programs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------ our arm
+KERNEL_BYTES = {
+    # algorithmic bytes of one launch as a function of (N shard bytes, C shard bytes): DESIGN.md "Kernels"
+    "hist_smem_kernel": lambda n, c: n,
+    "encode_kernel<false>": lambda n, c: n + c,
+    "encode_kernel<true>": lambda n, c: n + c,
+    "dec_sync_kernel": lambda n, c: c,
+    "dec_write_kernel": lambda n, c: c + n,
+    "decode_kernel": lambda n, c: c + n,
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from huffman_b200 import Codec
+    from huffman_b200.sharded import ShardedCodec, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_src = peaks()
+
+    n_total = workload_bytes(args.workload, args.bytes)
+    lo, hi = shard_bounds(n_total, world)[rank]
+    chunk = make_chunk(args.workload, n_total, lo, hi, dev)
+    n_shard = hi - lo
+    codec = Codec(local)
+    job = ShardedCodec(codec) if world > 1 else None
+
+    out_img = torch.empty(codec.compress_bound(n_shard) + 4096, dtype=torch.uint8, device=dev)
+    out_dec = torch.empty(n_shard + 64, dtype=torch.uint8, device=dev)
+
+    def do_compress():
+        if job is None:
+            return codec.compress(chunk, out_img)
+        return job.compress(chunk, n_total, 0, out_img)
+
+    def do_decompress(img):
+        if job is None:
+            return codec.decompress(img, out_dec)
+        return job.decompress(img, out_dec)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness of what is about to be timed (round trip; parity proper is tests/) ----
+    img = do_compress()
+    back = do_decompress(img)
+    torch.cuda.synchronize()
+    ok = back.numel() == n_shard and bool(torch.equal(back[:n_shard], chunk))
+    assert ok, "round trip of the bench workload failed"
+    c_shard = img.numel() if job is None else img.range_bytes
+
+    for _ in range(max(0, args.warmup - 1)):
+        img = do_compress()
+        do_decompress(img)
+
+    # ---- timed region ----
+    sampler = ClockSampler(local)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    codec.profile(True)
+    launches0 = codec.launch_count()
+    barrier()
+    sampler.start()
+    ev[0].record()
+    for i in range(args.steps):
+        img = do_compress()
+        ev[2 * i + 1].record()
+        do_decompress(img)
+        ev[2 * i + 2].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = codec.launch_count() - launches0
+    prof = codec.profile_read()
+    codec.profile(False)
+    t_total = ev[0].elapsed_time(ev[-1])
+    t_enc = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
+    t_dec = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
+    tt = torch.tensor([t_total, t_enc, t_dec, float(launches), float(c_shard)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_total, t_enc, t_dec = (float(x) for x in mx[:3])
+        launches, c_total = int(sm[3]), int(sm[4])
+    else:
+        c_total = c_shard
+    k = args.steps
+    value = 2 * n_total * k / (t_total * 1e-3) / 1e9
+    enc_gbs = n_total * k / (t_enc * 1e-3) / 1e9
+    dec_gbs = n_total * k / (t_dec * 1e-3) / 1e9
+
+    # ---- per-kernel shares and the dominant kernel's roofline (rank 0's launches) ----
+    kern = {}
+    tot_k = sum(ms for _, ms in prof.values()) or 1.0
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        e = {"launches": cnt, "avg_ms": ms / cnt, "share_of_kernel_time": ms / tot_k}
+        if name in KERNEL_BYTES:
+            b = KERNEL_BYTES[name](n_shard, c_shard)
+            e["alg_bytes"] = b
+            e["gbs"] = b / (ms / cnt * 1e-3) / 1e9
+            e["frac"] = e["gbs"] / hbm_peak
+        kern[name] = e
+    dom = next(iter(kern)) if kern else None
+    roof = None
+    if dom and "gbs" in kern[dom]:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom.split("<")[0])
+        roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"]}
+    phases = {"encode": {"gbs_alg": (2 * n_total + c_total) * k / (t_enc * 1e-3) / 1e9},
+              "decode": {"gbs_alg": (n_total + c_total) * k / (t_dec * 1e-3) / 1e9}}
+    for p in phases.values():
+        p["frac"] = p["gbs_alg"] / (hbm_peak * world)
+
+    # ---- end to end through the host-buffer C-ABI calls (pinned host memory, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        del back
+        e2e = run_e2e(args, codec, job, chunk, n_total, n_shard, world, dev, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = cpu_sample(args.workload, n_total, args.cpu_sample_mb << 20)
+        with tempfile.TemporaryDirectory() as td:
+            tc, tdx, kind, cores = cpu_reference_step(sample, td)
+        cpu = {"value": 2 * sample.size / (tc + tdx) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{sample.size} bytes of {args.workload} (equal pieces from each entropy segment), one archive + one extract",
+               "encode_gbs": sample.size / tc / 1e9, "decode_gbs": sample.size / tdx / 1e9,
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": args.warmup,
+            "ms_per_step": t_total / k, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "bytes": n_total, "compressed_bytes": c_total,
+                       "sharding": f"contiguous chunks x{world}", "l2": "inputs >> 126 MB L2, no flush needed",
+                       "step": "full compress then full decompress of the stream"},
+            "encode_gbs": enc_gbs, "decode_gbs": dec_gbs, "phases": phases,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+            "collectives_per_step": (job.collectives // (k + args.warmup + 0)) if job else 0,
+        }
+        print(json.dumps(line), flush=True)
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, codec, job, chunk, n_total, n_shard, world, dev, barrier):
+    """same step, but from and to pinned HOST buffers through hf_compress_host / hf_decompress_host
+    (N = 1) or H2D + sharded stages + D2H (N > 1)"""
+    import torch
+    import torch.distributed as dist
+    steps = max(1, min(args.steps, args.e2e_steps))
+    h_in = torch.empty(n_shard, dtype=torch.uint8).pin_memory()
+    h_in.copy_(chunk)
+    h_img = torch.empty(codec.compress_bound(n_shard) + 4096, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n_shard + 64, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n_shard, dtype=torch.uint8, device=dev) if job else None
+    d_img = torch.empty(codec.compress_bound(n_shard) + 4096, dtype=torch.uint8, device=dev) if job else None
+    d_out = torch.empty(n_shard + 64, dtype=torch.uint8, device=dev) if job else None
+    bytes_h2d = bytes_d2h = 0
+
+    def step():
+        nonlocal bytes_h2d, bytes_d2h
+        if job is None:
+            img = codec.compress_host(h_in, h_img)
+            back = codec.decompress_host(img, h_out)
+            bytes_h2d = n_shard + img.numel()
+            bytes_d2h = img.numel() + back.numel()
+            return back
+        d_in.copy_(h_in, non_blocking=True)
+        sl = job.compress(d_in, n_total, 0, d_img)
+        m = sl.range_bytes + 32
+        h_img[:m].copy_(sl.buf[:m], non_blocking=True)              # the compressed slice leaves the device ...
+        torch.cuda.current_stream().synchronize()
+        sl.buf[:m].copy_(h_img[:m], non_blocking=True)              # ... and comes back for the decode half
+        back, _, _ = job.decompress(sl, d_out)
+        h_out[:back.numel()].copy_(back, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        bytes_h2d = n_shard + m
+        bytes_d2h = m + back.numel()
+        return h_out[:back.numel()]
+
+    back = step()                                                   # warm-up + check
+    assert back.numel() == n_shard and bool(torch.equal(back[:n_shard], h_in)), "e2e round trip failed"
+    step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = max(a.elapsed_time(b), 0.0)
+    t = torch.tensor([max(ms * 1e-3, wall), float(bytes_h2d), float(bytes_d2h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t = torch.stack([mx[0], sm[1], sm[2]])
+    return {"value": 2 * n_total * steps / float(t[0]) / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": int(t[1]), "d2h_bytes_per_step": int(t[2]), "steps": steps,
+            "ms_per_step": float(t[0]) / steps * 1e3,
+            "path": "hf_compress_host + hf_decompress_host (pinned host buffers)" if job is None
+                    else "pinned H2D + sharded stages + D2H per rank"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mixed16g", choices=["mixed16g", "zipf1g"])
+    ap.add_argument("--bytes", type=int, default=0, help="override the workload size (testing)")
+    ap.add_argument("--cpu-sample-mb", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,10 @@ class HeaderInfo(ctypes.Structure):
                 ("status", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class KernelTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", ctypes.c_uint32), ("total_ms", ctypes.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/huffman_b200.h declares
 _P = ctypes.c_void_p
 _U64 = ctypes.c_uint64
@@ -47,6 +51,9 @@ _SIGS = {
     "hf_last_error": (ctypes.c_char_p, [_P]),
     "hf_version": (ctypes.c_char_p, []),
     "hf_launch_count": (_U64, [_P]),
+    "hf_profile_enable": (ctypes.c_int, [_P, ctypes.c_int]),
+    "hf_profile_read": (ctypes.c_int, [_P, ctypes.POINTER(KernelTime), ctypes.c_uint32,
+                                       ctypes.POINTER(ctypes.c_uint32)]),
     "hf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t]),
     "hf_host_free": (ctypes.c_int, [_P]),
     "hf_codebook_bytes": (ctypes.c_size_t, []),

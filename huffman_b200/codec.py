@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CbInfo, HeaderInfo, HuffmanError, NSYM
+from ._lib import CbInfo, HeaderInfo, HuffmanError, KernelTime, NSYM
 
 
 def _ptr(t):
@@ -77,6 +77,17 @@ class Codec:
 
     def launch_count(self):
         return int(self.lib.hf_launch_count(self.ctx))
+
+    def profile(self, on=True):
+        """bracket every kernel launch of this context with CUDA events (bench.py's roofline)"""
+        self._check(self.lib.hf_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, total device ms)} since the last read; synchronises"""
+        buf = (KernelTime * 64)()
+        n = ctypes.c_uint32(0)
+        self._check(self.lib.hf_profile_read(self.ctx, buf, 64, ctypes.byref(n)))
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n.value)}
 
     def sync(self):
         self._check(self.lib.hf_sync(self.ctx))

@@ -40,6 +40,20 @@ int ensure_ws(Ctx *c, size_t bytes)
     return HF_OK;
 }
 
+void prof_begin(Ctx *c, const char *name)
+{
+    if (c->prof_n >= PROF_CAP) return;
+    c->prof_name[c->prof_n] = name;
+    if (cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream) == cudaSuccess) c->prof_open = true;
+}
+
+void prof_end(Ctx *c)
+{
+    cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream);
+    c->prof_n++;
+    c->prof_open = false;
+}
+
 static int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes)
 {
     if (bytes <= *have) return HF_OK;
@@ -119,6 +133,11 @@ int hf_ctx_destroy(hf_ctx *ctx)
     if (c->d_tab) cudaFree(c->d_tab);
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->prof_ev) {
+        for (uint32_t i = 0; i < 2 * PROF_CAP; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
+        free(c->prof_ev);
+        free(c->prof_name);
+    }
     free(c);
     return HF_OK;
 }
@@ -141,6 +160,48 @@ int hf_sync(hf_ctx *ctx)
 
 const char *hf_last_error(hf_ctx *ctx) { return ctx ? CTX(ctx)->err : "no context"; }
 uint64_t hf_launch_count(hf_ctx *ctx) { return ctx ? CTX(ctx)->launches : 0; }
+
+int hf_profile_enable(hf_ctx *ctx, int on)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (on && !c->prof_ev) {
+        c->prof_ev = (cudaEvent_t *)calloc(2 * PROF_CAP, sizeof(cudaEvent_t));
+        c->prof_name = (const char **)calloc(PROF_CAP, sizeof(char *));
+        if (!c->prof_ev || !c->prof_name) return set_err(c, HF_ERR_ARG, "hf_profile_enable: out of memory");
+        for (uint32_t i = 0; i < 2 * PROF_CAP; i++) HF_CUDA(c, cudaEventCreate(&c->prof_ev[i]));
+    }
+    c->prof_on = on != 0;
+    c->prof_open = false;
+    c->prof_n = 0;
+    return HF_OK;
+}
+
+int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *n_out)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!n_out || (cap && !out)) return set_err(c, HF_ERR_ARG, "hf_profile_read: null pointer");
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < c->prof_n; i++) {
+        float ms = 0.f;
+        HF_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        uint32_t k = 0;
+        while (k < n && strncmp(out[k].name, c->prof_name[i], sizeof(out[k].name) - 1) != 0) k++;
+        if (k == n) {
+            if (n >= cap) continue;
+            memset(&out[k], 0, sizeof(out[k]));
+            strncpy(out[k].name, c->prof_name[i], sizeof(out[k].name) - 1);
+            n++;
+        }
+        out[k].launches++;
+        out[k].total_ms += ms;
+    }
+    *n_out = n;
+    c->prof_n = 0;
+    return HF_OK;
+}
 
 int hf_host_alloc(void **h_ptr, size_t bytes)
 {

@@ -393,11 +393,11 @@ int launch_codebook(Ctx *c, const unsigned long long *d_hist, Codebook *d_cb)
     if (rc) return rc;
     CbWork *w = reinterpret_cast<CbWork *>(c->ws);
     HF_CUDA(c, cudaMemsetAsync(d_cb, 0, codebook_alloc_bytes(), c->stream));
-    cb_sort_tree_kernel<<<1, CB_THREADS, 0, c->stream>>>(d_hist, w, d_cb);
+    HF_PROF(c, "cb_sort_tree_kernel"); cb_sort_tree_kernel<<<1, CB_THREADS, 0, c->stream>>>(d_hist, w, d_cb);
     HF_LAUNCH_CHECK(c);
-    cb_codes_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_hist, w, d_cb);
+    HF_PROF(c, "cb_codes_kernel"); cb_codes_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_hist, w, d_cb);
     HF_LAUNCH_CHECK(c);
-    cb_entry_scan_kernel<<<1, CB_THREADS, 0, c->stream>>>(w, entry_off_of(d_cb));
+    HF_PROF(c, "cb_entry_scan_kernel"); cb_entry_scan_kernel<<<1, CB_THREADS, 0, c->stream>>>(w, entry_off_of(d_cb));
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -406,7 +406,7 @@ int launch_shard_bits(Ctx *c, const unsigned long long *d_hist, const Codebook *
                       unsigned long long *d_bits)
 {
     HF_CUDA(c, cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), c->stream));
-    shard_bits_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_hist, d_cb, d_bits);
+    HF_PROF(c, "shard_bits_kernel"); shard_bits_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_hist, d_cb, d_bits);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -420,7 +420,7 @@ int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t 
     if (capacity < 12) return set_err(c, HF_ERR_CAPACITY, "hf_header_pack: capacity %llu too small",
                                       (unsigned long long)capacity);
     HF_CUDA(c, cudaMemsetAsync(d_file, 0, z, c->stream));
-    header_pack_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, entry_off_of(const_cast<Codebook *>(d_cb)),
+    HF_PROF(c, "header_pack_kernel"); header_pack_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, entry_off_of(const_cast<Codebook *>(d_cb)),
                                                          n_bytes, last_byte, d_file);
     HF_LAUNCH_CHECK(c);
     return HF_OK;

@@ -89,7 +89,16 @@ struct Ctx {
     void *d_cb;
     void *d_tab;
     void *d_hist;
+    // optional per-kernel timing (hf_profile_*): event pairs around every launch
+    bool prof_on;
+    bool prof_open;                 // a begin event is pending
+    uint32_t prof_n;                // recorded pairs
+    cudaEvent_t *prof_ev;           // 2 * PROF_CAP events, created on first enable
+    const char **prof_name;         // PROF_CAP static strings
 };
+constexpr uint32_t PROF_CAP = 8192;
+void prof_begin(Ctx *c, const char *name);
+void prof_end(Ctx *c);
 
 int set_err(Ctx *c, int code, const char *fmt, ...);
 int ensure_ws(Ctx *c, size_t bytes);
@@ -102,9 +111,16 @@ int ensure_ws(Ctx *c, size_t bytes);
                                cudaGetErrorString(_e));                                 \
     } while (0)
 
+// HF_PROF(ctx, "kernel") goes directly before a launch, HF_LAUNCH_CHECK(ctx) directly after
+#define HF_PROF(ctx, name)                                                              \
+    do {                                                                                \
+        if ((ctx)->prof_on) hf::prof_begin((ctx), (name));                              \
+    } while (0)
+
 #define HF_LAUNCH_CHECK(ctx)                                                            \
     do {                                                                                \
         (ctx)->launches++;                                                              \
+        if ((ctx)->prof_open) hf::prof_end((ctx));                                      \
         HF_CUDA((ctx), cudaGetLastError());                                             \
     } while (0)
 

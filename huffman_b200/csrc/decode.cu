@@ -726,11 +726,11 @@ static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
     // zero everything but the (large) long list; t2 zero = invalid
     HF_CUDA(c, cudaMemsetAsync(d_tab, 0, offsetof(DecodeTable, longs), c->stream));
     HF_CUDA(c, cudaMemsetAsync(src->len_mask, 0, sizeof(src->len_mask), c->stream));
-    dt_depth_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab, src->len_mask);
+    HF_PROF(c, "dt_depth_kernel"); dt_depth_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab, src->len_mask);
     HF_LAUNCH_CHECK(c);
-    dt_offsets_kernel<<<1, 1024, 0, c->stream>>>(src, d_tab, src->len_mask);
+    HF_PROF(c, "dt_offsets_kernel"); dt_offsets_kernel<<<1, 1024, 0, c->stream>>>(src, d_tab, src->len_mask);
     HF_LAUNCH_CHECK(c);
-    dt_fill_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab);
+    HF_PROF(c, "dt_fill_kernel"); dt_fill_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -740,7 +740,7 @@ int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab)
     int rc = ensure_ws(c, sizeof(TabSrc));
     if (rc) return rc;
     TabSrc *src = reinterpret_cast<TabSrc *>(c->ws);
-    dt_from_codebook_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, src);
+    HF_PROF(c, "dt_from_codebook_kernel"); dt_from_codebook_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, src);
     HF_LAUNCH_CHECK(c);
     return build_tables(c, src, d_tab);
 }
@@ -758,9 +758,9 @@ int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, Deco
     }
     // status of an earlier use must not leak into this parse
     HF_CUDA(c, cudaMemsetAsync(&d_tab->status, 0, sizeof(uint32_t), c->stream));
-    dec_parse_kernel<<<1, 1024, HDR_STAGE + 32, c->stream>>>(d_file, file_bytes, src, d_tab, d_info);
+    HF_PROF(c, "dec_parse_kernel"); dec_parse_kernel<<<1, 1024, HDR_STAGE + 32, c->stream>>>(d_file, file_bytes, src, d_tab, d_info);
     HF_LAUNCH_CHECK(c);
-    dec_entries_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_file, file_bytes, src);
+    HF_PROF(c, "dec_entries_kernel"); dec_entries_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_file, file_bytes, src);
     HF_LAUNCH_CHECK(c);
     return build_tables(c, src, d_tab);
 }
@@ -789,17 +789,17 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
     HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
 
     uint16_t *out16 = reinterpret_cast<uint16_t *>(d_out);
-    dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, out16);
+    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, out16);
     HF_LAUNCH_CHECK(c);
-    dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch);
+    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch);
     HF_LAUNCH_CHECK(c);
     if (nch > 1) {
-        dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
+        HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
         HF_LAUNCH_CHECK(c);
-        dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
+        HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch);
         HF_LAUNCH_CHECK(c);
     }
-    dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch);
+    HF_PROF(c, "dec_scan_kernel"); dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch);
     HF_LAUNCH_CHECK(c);
     const size_t wsmem = (CHUNK_WORDS + CHUNK_PAD_WORDS + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
     static bool wattr = false;
@@ -807,7 +807,7 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
         HF_CUDA(c, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
         wattr = true;
     }
-    dec_write_kernel<<<(unsigned)nch, DEC_THREADS, wsmem, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16);
+    HF_PROF(c, "dec_write_kernel"); dec_write_kernel<<<(unsigned)nch, DEC_THREADS, wsmem, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -311,12 +311,12 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     HF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, encode_kernel<true>, ENC_THREADS, smem_long));
     if (maxlen_hint == 0 || maxlen_hint <= ENC32_MAX_LEN) {
         uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)c->sm_count * (occ_fast > 0 ? occ_fast : 1));
-        encode_kernel<false><<<grid, ENC_THREADS, smem_fast, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
+        HF_PROF(c, "encode_kernel<false>"); encode_kernel<false><<<grid, ENC_THREADS, smem_fast, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
         HF_LAUNCH_CHECK(c);
     }
     if (maxlen_hint == 0 || maxlen_hint > ENC32_MAX_LEN) {
         uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)c->sm_count * (occ_long > 0 ? occ_long : 1));
-        encode_kernel<true><<<grid, ENC_THREADS, smem_long, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
+        HF_PROF(c, "encode_kernel<true>"); encode_kernel<true><<<grid, ENC_THREADS, smem_long, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
         HF_LAUNCH_CHECK(c);
     }
     return HF_OK;

@@ -106,7 +106,7 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
     const uint16_t *p = reinterpret_cast<const uint16_t *>(d_in);
     if (n_bytes < HIST_SMALL_BYTES) {
         int blocks = (int)((n_sym + 255) / 256);
-        hist_scalar_kernel<<<blocks, 256, 0, c->stream>>>(p, n_sym, d_hist);
+        HF_PROF(c, "hist_scalar_kernel"); hist_scalar_kernel<<<blocks, 256, 0, c->stream>>>(p, n_sym, d_hist);
         HF_LAUNCH_CHECK(c);
         return HF_OK;
     }
@@ -115,9 +115,9 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
     if (head > n_sym) head = n_sym;
     uint64_t n_vec = (n_sym - head) / 8;
     uint64_t tail = n_sym - head - n_vec * 8;
-    if (head) { hist_scalar_kernel<<<1, 32, 0, c->stream>>>(p, head, d_hist); HF_LAUNCH_CHECK(c); }
+    if (head) { HF_PROF(c, "hist_scalar_kernel"); hist_scalar_kernel<<<1, 32, 0, c->stream>>>(p, head, d_hist); HF_LAUNCH_CHECK(c); }
     if (tail) {
-        hist_scalar_kernel<<<1, 32, 0, c->stream>>>(p + head + n_vec * 8, tail, d_hist);
+        HF_PROF(c, "hist_scalar_kernel"); hist_scalar_kernel<<<1, 32, 0, c->stream>>>(p + head + n_vec * 8, tail, d_hist);
         HF_LAUNCH_CHECK(c);
     }
     if (n_vec) {
@@ -133,10 +133,10 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
                                             HIST_WORDS * 4));
             attr_set = true;
         }
-        hist_smem_kernel<<<grid, HIST_THREADS, HIST_WORDS * 4, c->stream>>>(
+        HF_PROF(c, "hist_smem_kernel"); hist_smem_kernel<<<grid, HIST_THREADS, HIST_WORDS * 4, c->stream>>>(
             reinterpret_cast<const uint4 *>(p + head), n_vec, (uint32_t *)c->ws, d_hist);
         HF_LAUNCH_CHECK(c);
-        hist_reduce_kernel<<<HIST_WORDS / 256, 256, 0, c->stream>>>((const uint32_t *)c->ws, grid, d_hist);
+        HF_PROF(c, "hist_reduce_kernel"); hist_reduce_kernel<<<HIST_WORDS / 256, 256, 0, c->stream>>>((const uint32_t *)c->ws, grid, d_hist);
         HF_LAUNCH_CHECK(c);
     }
     return HF_OK;

@@ -79,6 +79,18 @@ const char *hf_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t hf_launch_count(hf_ctx *ctx);
 
+/* Per-kernel device times, for bench.py's roofline: while enabled, every kernel launch of this
+ * context is bracketed by CUDA events on the context's stream (the reference prints wall
+ * timers instead, C:356-399, C:492-593, h:697-698).  hf_profile_read synchronises, sums the
+ * recorded launches by kernel name into out[0..*n_out) and clears the record. */
+typedef struct {
+    char name[48];
+    uint32_t launches;
+    float total_ms;
+} hf_kernel_time_t;
+int hf_profile_enable(hf_ctx *ctx, int on);
+int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *n_out);
+
 /* pinned host buffers for the host-facing calls (C:343 uses cudaHostAlloc) */
 int hf_host_alloc(void **h_ptr, size_t bytes);
 int hf_host_free(void *h_ptr);
