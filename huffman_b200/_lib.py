@@ -70,6 +70,9 @@ _SIGS = {
     "hf_parse_header": (ctypes.c_int, [_P, _P, _U64, _P, ctypes.POINTER(HeaderInfo)]),
     "hf_decode_table_from_codebook": (ctypes.c_int, [_P, _P, _P]),
     "hf_decode": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P]),
+    "hf_range_overflow": (ctypes.c_int, [_P, _P, _U64, _U64, _P, _P]),
+    "hf_decode_range": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P, _U64, _P]),
+    "hf_set_decode_mode": (ctypes.c_int, [_P, ctypes.c_int]),
     "hf_decompress": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_compress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_decompressed_size_host": (ctypes.c_int, [_P, _U64, ctypes.POINTER(_U64)]),

@@ -147,6 +147,33 @@ class Codec:
         self._check(self.lib.hf_decode(self.ctx, _ptr(stream_buf), stream_buf.numel(), start_bit, n_symbols,
                                        _ptr(table), _ptr(out)))
 
+    def range_overflow(self, buf, range_bytes, halo_bytes, table, result=None):
+        """hf_range_overflow: device int64[4], [1] = bits by which the last code word that starts inside
+        buf[:range_bytes] runs past the range end (found speculatively from the last 16 KiB)"""
+        if result is None:
+            result = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self._check(self.lib.hf_range_overflow(self.ctx, _ptr(buf), range_bytes, halo_bytes, _ptr(table), _ptr(result)))
+        return result
+
+    def decode_range(self, buf, range_bytes, halo_bytes, first_bit, table, out, result=None):
+        """hf_decode_range: the code words starting inside buf[:range_bytes], the first one at first_bit;
+        returns the device int64[4] result: -, overflow past the range, symbols, flags"""
+        if result is None:
+            result = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self._check(self.lib.hf_decode_range(self.ctx, _ptr(buf), range_bytes, halo_bytes, first_bit, _ptr(table),
+                                             _ptr(out), out.numel() // 2, _ptr(result)))
+        return result
+
+    def set_decode_mode(self, exact_only):
+        """True: always the exact multi-pass decoder; False (default): single pass with on-device fallback"""
+        self._check(self.lib.hf_set_decode_mode(self.ctx, 1 if exact_only else 0))
+
+    def codebook_info(self, cb):
+        return cb.info()
+
+    def header_bound(self, n_bytes):
+        return 4 + 11 * min(NSYM, n_bytes // 2) + 8 + 4
+
     def decompress(self, image, out=None):
         size = ctypes.c_uint64(0)
         if out is None:

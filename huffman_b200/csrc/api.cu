@@ -382,6 +382,33 @@ int hf_decode(hf_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint6
                          reinterpret_cast<const DecodeTable *>(d_decode_table), d_out);
 }
 
+int hf_decode_range(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, uint64_t first_bit,
+                    const void *d_decode_table, uint8_t *d_out, uint64_t out_symbols, uint64_t *d_result)
+{
+    NEED_CTX(ctx);
+    if (!d_range || !d_decode_table || !d_out || !d_result) return set_err(CTX(ctx), HF_ERR_ARG, "hf_decode_range: null pointer");
+    return launch_decode_range(CTX(ctx), d_range, range_bytes, halo_bytes, first_bit, false,
+                               reinterpret_cast<const DecodeTable *>(d_decode_table), d_out, out_symbols,
+                               reinterpret_cast<unsigned long long *>(d_result));
+}
+
+int hf_range_overflow(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
+                      const void *d_decode_table, uint64_t *d_result)
+{
+    NEED_CTX(ctx);
+    if (!d_range || !d_decode_table || !d_result) return set_err(CTX(ctx), HF_ERR_ARG, "hf_range_overflow: null pointer");
+    return launch_decode_range(CTX(ctx), d_range, range_bytes, halo_bytes, 0, true,
+                               reinterpret_cast<const DecodeTable *>(d_decode_table), nullptr, 0,
+                               reinterpret_cast<unsigned long long *>(d_result));
+}
+
+int hf_set_decode_mode(hf_ctx *ctx, int exact_only)
+{
+    NEED_CTX(ctx);
+    CTX(ctx)->decode_exact_only = exact_only != 0;
+    return HF_OK;
+}
+
 // flags written by the decode kernels (decode.cu: DecWork.flags) sit at ws + 8 MiB
 static int check_decode_flags(Ctx *c)
 {

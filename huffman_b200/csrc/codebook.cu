@@ -289,6 +289,10 @@ __global__ void cb_codes_kernel(const unsigned long long *__restrict__ hist, CbW
         cb->len[sym] = (uint8_t)len;
         cb->code[sym] = code;
         cb->enc32[sym] = len <= ENC32_MAX_LEN ? ((len << 27) | (uint32_t)code) : 0xFFFFFFFFu;
+        const uint32_t v24 = len <= 23 ? ((1u << len) | (uint32_t)code) : 0u;
+        const uint32_t fsym = sym ^ (sym >> 8);                 // the encoder's bank-spreading index (encode.cu fold16)
+        cb->p16[fsym] = (uint16_t)v24;
+        cb->p8[fsym] = (uint8_t)(v24 >> 16);
         w->entry_bits[k] = 24 + len;
         tb = 24 + len;
         pb = hist[sym] * len;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stddef.h>
 
 #include "../../include/huffman_b200.h"
 
@@ -32,7 +33,14 @@ struct Codebook {
     uint8_t len[NSYM];         // by symbol, 0 when absent
     uint32_t enc32[NSYM];      // by symbol
     unsigned long long code[NSYM];   // by symbol, right aligned, root->leaf
+    // the encoder's shared-memory table: (1 << len) | code for 1 <= len <= 23 (0 = longer or absent),
+    // low 16 bits in p16, high 8 bits in p8, both indexed by sym ^ (sym >> 8); contiguous and 16-byte
+    // aligned (copied to shared memory with 128-bit loads)
+    alignas(16) uint16_t p16[NSYM];
+    uint8_t p8[NSYM];
 };
+static_assert(offsetof(Codebook, p16) % 16 == 0, "encoder planes must be 16-byte aligned");
+static_assert(offsetof(Codebook, p8) == offsetof(Codebook, p16) + NSYM * 2, "encoder planes must be contiguous");
 
 // ---- device-resident decode tables (hf_decode_table_bytes) ------------------------
 // Level 1: K1-bit direct table (copied to shared memory by the decode kernels).
@@ -41,14 +49,15 @@ struct Codebook {
 //   0       hole (incomplete code)
 // Level 2: per-prefix direct tables, sub_bits <= k2cap (12, or 8 when 12 would overflow t2).
 //   leaf    (sym << 8) | total_len
-//   0xFFFFFFFF  escape: the code is longer than K1 + sub_bits -> linear list `longs`
+//   list    0x80000080 | (i << 8): codes longer than K1 + sub_bits that share this slot's prefix form a
+//           linked list through `longs`, head longs[i] (a handful of entries: prefix codes)
 constexpr uint32_t K1 = 12;
 constexpr uint32_t K2MAX = 12;
 constexpr uint32_t T2_CAP = 1u << 20;          // entries; 2^K1 prefixes x 2^8 always fits
 struct LongCode {
     unsigned long long code_left;               // left aligned in 64 bits
-    uint32_t len;
-    uint32_t sym;
+    uint32_t leaf;                              // (sym << 8) | len
+    uint32_t next;                              // next list entry (same encoding as the slot), 0 at the end
 };
 struct DecodeTable {
     uint32_t U;
@@ -89,6 +98,7 @@ struct Ctx {
     void *d_cb;
     void *d_tab;
     void *d_hist;
+    bool decode_exact_only;         // hf_set_decode_mode(1): skip the single-pass decoder (tests)
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
     bool prof_open;                 // a begin event is pending
@@ -138,6 +148,9 @@ int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, Deco
 int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab);
 int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
                   uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out);
+int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, uint64_t first_bit,
+                        bool tail_only, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
+                        unsigned long long *d_result);
 
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__

@@ -1,0 +1,109 @@
+// decode_common.cuh — bit readers and the table walk shared by the exact decoder (decode.cu) and the
+// single-pass decoder (decode_fast.cu).  Private to libhuffb200.
+#pragma once
+#include "common.cuh"
+
+namespace hf {
+
+constexpr uint32_t E_SUB = 0x80u;                               // entry flag: sub-table / escape
+constexpr uint32_t E_LIST = 0x80000000u;                           // level-2 slot: head of a long-code list
+
+// -----------------------------------------------------------------------------------
+// bit access.  Fetch functors return big-endian 32-bit word i of some bit string.
+struct SmemFetch {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return w[i]; }
+};
+struct GlobalFetch {                    // frame words straight from global memory, zero past the end
+    const uint8_t *frame;
+    unsigned long long frame_bytes;
+    unsigned long long word0;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const
+    {
+        unsigned long long b = (word0 + i) * 4ull;
+        if (b + 4 <= frame_bytes) return bswap32(*reinterpret_cast<const uint32_t *>(frame + b));
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++)
+            if (b + k < frame_bytes) v |= (uint32_t)frame[b + k] << (24 - 8 * k);
+        return v;
+    }
+};
+
+template <typename F>
+struct BitReader {
+    F f;
+    uint32_t wi;                        // next word to pull
+    unsigned long long win;             // upcoming bits, left aligned
+    uint32_t avail;                     // valid bits in win (kept > 32)
+    __device__ __forceinline__ void init(uint32_t bitpos)
+    {
+        wi = bitpos >> 5;
+        uint32_t sh = bitpos & 31;
+        win = (((unsigned long long)f(wi) << 32) | f(wi + 1)) << sh;
+        avail = 64 - sh;
+        wi += 2;
+        if (avail <= 32) { win |= (unsigned long long)f(wi++) << (32 - avail); avail += 32; }
+    }
+    __device__ __forceinline__ void consume(uint32_t n)     // n <= 32 per call
+    {
+        win <<= n;
+        avail -= n;
+        if (avail <= 32) { win |= (unsigned long long)f(wi++) << (32 - avail); avail += 32; }
+    }
+    __device__ __forceinline__ void skip(uint32_t n)
+    {
+        while (n > 32) { consume(32); n -= 32; }
+        consume(n);
+    }
+};
+
+template <typename F>
+__device__ __forceinline__ unsigned long long peek64(const F &f, uint32_t bitpos)
+{
+    uint32_t i = bitpos >> 5, sh = bitpos & 31;
+    unsigned long long hi = ((unsigned long long)f(i) << 32) | f(i + 1);
+    if (sh == 0) return hi;
+    return (hi << sh) | ((unsigned long long)f(i + 2) >> (32 - sh));
+}
+
+struct TabView {
+    const uint32_t *t1;                 // shared (kernels A, C) or global (kernel B)
+    const uint32_t *t2;
+    const LongCode *longs;
+    uint32_t n_long;
+};
+
+// one code word at the reader's position; returns (sym << 8) | len, len >= 1
+template <typename F>
+__device__ __forceinline__ uint32_t decode_one(const TabView &T, const BitReader<F> &r, uint32_t bitpos,
+                                               uint32_t &bad)
+{
+    uint32_t e = T.t1[(uint32_t)(r.win >> (64 - K1))];
+    if (e & E_SUB) {
+        const uint32_t sb = e & 31u;
+        const uint32_t idx2 = (uint32_t)((r.win << K1) >> (64 - sb));
+        e = __ldg(&T.t2[(e >> 8) + idx2]);
+        if (e & E_LIST) {               // longer than K1 + sub bits: walk the slot's list of long codes
+            const unsigned long long w64 = peek64(r.f, bitpos);
+            uint32_t cur = e;
+            e = 0;
+            while (cur & E_LIST) {
+                const LongCode lc = T.longs[(cur >> 8) & 0xFFFFu];
+                if (((w64 ^ lc.code_left) >> (64 - (lc.leaf & 0x7Fu))) == 0) { e = lc.leaf; break; }
+                cur = lc.next;
+            }
+        }
+    }
+    if (e == 0) { bad = 1; e = 1; }     // hole in the code: flag it, step one bit so the walk ends
+    return e;
+}
+
+__device__ __forceinline__ uint32_t spec_start(unsigned long long X, unsigned long long F0, uint32_t g)
+{   // first offset >= 0 from frame bit X at which a code word can start (boundaries are F0 + k*g)
+    if (g <= 1) return 0;
+    uint32_t r = (uint32_t)((X - F0) % g);
+    return r ? g - r : 0;
+}
+
+
+}  // namespace hf

@@ -1,21 +1,32 @@
-// encode.cu — single-pass Huffman encoder: code-length lookup, decoupled-lookback
-// exclusive scan of bit offsets and bit packing in ONE kernel.
+// encode.cu — single-pass Huffman encoder: code lookup, decoupled-lookback exclusive scan of
+// the bit offsets and bit packing in ONE kernel.
 //
 // Replaces populateCWLength + thrust::transform_inclusive_scan + encodeFromCW + the host
 // tail flush (/root/reference/Compressor.cu:50-74, :152-313, :541-601, :673-684): the
 // reference materialises 12 bytes of scratch per symbol and then binary-searches the
 // offsets once per OUTPUT byte.  Here the input is read once and the output written once.
 //
-// Per tile of 8192 symbols (512 threads x 2 groups x 8 symbols, one 128-bit load each):
-//   1. gather (len, code) per symbol from the 256 KiB enc32 table (L1/L2 resident),
-//      sum the lengths, CTA-wide exclusive scan of both groups at once (packed 2 x 32 bit);
-//   2. warp 0 publishes the tile's bit count and resolves its global bit offset by
+// The code table of the 65,536-symbol alphabet lives in SHARED memory: 24-bit entries
+// (1 << len) | code  for len <= 23 — the leading one bit carries the length — stored as two
+// planes (u16 low part, u8 high part: 192 KiB of the SM's 227 KiB) and indexed by the symbol
+// with its low byte XOR-folded with its high byte, so that skewed first bytes (text, Zipf) still
+// spread over the 32 banks.  Gathers from shared memory cost bank conflicts only; the same gathers
+// from global memory cost one L1 wavefront per distinct line and bounded the first version of this
+// kernel.  Entry 0 means "longer than 23 bits" (or absent): (len, code) come from global memory.
+//
+// One persistent 1024-thread CTA per SM = 4 independent teams of 256 threads (named barriers),
+// each looping over tiles of 4096 symbols claimed from an atomic counter; the next tile's index
+// and input are fetched while the current tile is packed:
+//   1. 2 x 128-bit loads per thread (8 symbols each), table lookup, length sums,
+//      team-wide exclusive scan of both groups at once (packed 2 x 32 bit);
+//   2. warp 0 of the team publishes the tile's bit count and resolves its global bit offset by
 //      decoupled look-back over the predecessors' descriptors (acquire/release);
-//   3. every thread streams its codes through a 64-bit funnel accumulator into a shared
-//      staging buffer laid out at the tile's 128-bit phase, so that
-//   4. the staging buffer is copied out with aligned 128-bit stores.  The word shared with
-//      the previous tile is completed by THIS tile from the predecessor's published tail
-//      word, so every output word is written exactly once: no memset, no global atomics.
+//   3. every symbol's code is OR-ed (shared-memory atomics, no carried state, no divergent flush)
+//      into the team's staging window (2048 words at the tile's 128-bit phase); a tile whose bits
+//      exceed the window (more than ~16 bits per symbol) is packed window by window;
+//   4. a 32-bit word belongs to the tile that holds its first bit: the owner completes its last,
+//      partial word by encoding the symbols that FOLLOW the tile until the word is full, so tiles
+//      exchange nothing but the look-back prefix; windows leave with aligned 128-bit stores.
 // Bits before the start phase in the first byte are preserved; the last byte is zero padded.
 //
 // Algorithmic bytes: N read + C written.  Roofline: HBM.
@@ -23,136 +34,170 @@
 
 namespace hf {
 
-constexpr int ENC_THREADS = 512;
+constexpr int ENC_TEAM = 256;                       // threads per team
+constexpr int ENC_NT = 3;                           // teams per CTA
+constexpr int ENC_THREADS = ENC_TEAM * ENC_NT;
 constexpr int ENC_GROUPS = 2;                       // 8-symbol groups per thread
-constexpr uint32_t ENC_TILE_SYMS = ENC_THREADS * 8 * ENC_GROUPS;    // 8192
+constexpr uint32_t ENC_TILE_SYMS = ENC_TEAM * 8 * ENC_GROUPS;       // 4096
+constexpr uint32_t ENC_WIN = 2048;                  // staging words per team (multiple of 4)
+constexpr uint32_t ENC_PLANE_BYTES = NSYM * 3;      // p16 + p8
+constexpr size_t ENC_SMEM = ENC_PLANE_BYTES + (size_t)ENC_NT * ENC_WIN * 4;
 constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_INCL = 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
+constexpr uint32_t V_FALLBACK = 0x80000000u;        // v = V_FALLBACK | symbol: take (len, code) from global memory
+constexpr unsigned long long NOT_FINAL = ~0ull;
 
 struct EncWork {                                    // lives in ctx->ws, zeroed per launch
     unsigned long long counter;                     // next tile
     unsigned long long error;
-    // followed by desc[ntiles], tail[ntiles]
+    // followed by desc[ntiles]
 };
 
-template <bool LONG>
-struct EncCfg {
-    static constexpr uint32_t MAXLEN = LONG ? 64 : ENC32_MAX_LEN;
-    static constexpr uint32_t STAGE_WORDS = ENC_TILE_SYMS * MAXLEN / 32 + 8;   // + 128-bit phase + slack
-};
-
-// append `len` (<= 32) bits of `code` to the thread's funnel; flush full words to staging
-__device__ __forceinline__ void put_bits(uint32_t *stage, unsigned long long &acc, uint32_t &nb, uint32_t &w,
-                                         bool &shared_first, uint32_t code, uint32_t len)
+__device__ __forceinline__ void team_sync(uint32_t team)
 {
-    acc |= (unsigned long long)code << (64 - nb - len);       // nb < 32, len <= 32; len == 0 adds nothing
-    nb += len;
-    if (nb >= 32) {
-        uint32_t word = (uint32_t)(acc >> 32);
-        if (shared_first) { atomicOr(&stage[w], word); shared_first = false; }
-        else stage[w] = word;
-        w++;
-        acc <<= 32;
-        nb -= 32;
-    }
+    asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(ENC_TEAM) : "memory");
 }
 
-template <bool LONG>
-__global__ void __launch_bounds__(ENC_THREADS)
+__device__ __forceinline__ uint32_t fold16(uint32_t sym) { return sym ^ (sym >> 8); }      // involution on 16 bits
+
+// OR `len` (<= 32) bits, given left aligned in c32, into the window at tile-relative bit `pos`
+__device__ __forceinline__ void or_code(uint32_t *stage, uint32_t wbase, uint32_t pos, uint32_t c32, uint32_t len)
+{
+    const uint32_t sh = pos & 31, w = (pos >> 5) - wbase;
+    if (w < ENC_WIN) atomicOr(&stage[w], c32 >> sh);
+    if (sh + len > 32 && w + 1 < ENC_WIN) atomicOr(&stage[w + 1], __funnelshift_r(0u, c32, sh));
+}
+
+// (len, code) of one symbol from the shared planes, or from the global codebook when it is not there
+__device__ __forceinline__ void lookup_slow(const uint16_t *p16, const uint8_t *p8, const Codebook *cb, uint32_t sym,
+                                            uint32_t &len, unsigned long long &code)
+{
+    const uint32_t f = fold16(sym);
+    const uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
+    if (x) { len = 31 - __clz(x); code = x ^ (1u << len); }
+    else { len = cb->len[sym]; code = cb->code[sym]; }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 1)
 encode_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb,
               uint8_t *stream, uint64_t start_bit, EncWork *work, uint32_t ntiles)
 {
-    // variant selection on the device keeps hf_encode asynchronous (see launch_encode)
-    if ((cb->maxlen > ENC32_MAX_LEN) != LONG) return;
+    extern __shared__ __align__(16) uint8_t enc_smem[];
+    const uint16_t *p16 = reinterpret_cast<const uint16_t *>(enc_smem);
+    const uint8_t *p8 = enc_smem + NSYM * 2;
+    __shared__ unsigned long long s_scan[ENC_NT][12];
+    __shared__ unsigned long long s_bcast[ENC_NT];
+    __shared__ unsigned long long s_final[ENC_NT];
+    __shared__ uint32_t s_tile[ENC_NT];
 
-    extern __shared__ __align__(16) uint32_t stage[];
-    __shared__ unsigned long long s_scan[20];
-    __shared__ unsigned long long s_bcast[2];
-    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, team = tid / ENC_TEAM, ttid = tid % ENC_TEAM;
+    const uint32_t lane = tid & 31, twid = ttid >> 5;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(enc_smem + ENC_PLANE_BYTES) + team * ENC_WIN;
+    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
+
+    // the table planes: one coalesced copy per CTA, L2 resident after the first
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cb->p16);
+        uint4 *dst = reinterpret_cast<uint4 *>(enc_smem);
+        for (uint32_t i = tid; i < ENC_PLANE_BYTES / 16; i += ENC_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (ttid == 0) s_tile[team] = (uint32_t)atomicAdd(&work->counter, 1ull);
+    __syncthreads();
 
     unsigned long long *desc = reinterpret_cast<unsigned long long *>(work + 1);
-    unsigned long long *tails = desc + ntiles;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
     // aligned frame: bit 0 of the frame is the 16-byte boundary at or below `stream`
     uint8_t *frame = reinterpret_cast<uint8_t *>((uintptr_t)stream & ~(uintptr_t)15);
     const unsigned long long bit0 = ((uintptr_t)stream & 15) * 8ull + start_bit;   // first payload bit, frame coordinates
-    const uint32_t *enc32 = cb->enc32;
+    const bool in_aligned = ((uintptr_t)in_bytes & 15) == 0;
 
-    for (;;) {
-        __syncthreads();                            // staging / s_tile reuse
-        if (tid == 0) s_tile = (uint32_t)atomicAdd(&work->counter, 1ull);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles) break;
+    // raw input of a tile: full tiles of an aligned input come as 2 x 128 bit per thread
+    uint4 raw[ENC_GROUPS];
+    auto is_full = [&](uint32_t t) { return in_aligned && t < ntiles && (uint64_t)(t + 1) * ENC_TILE_SYMS <= n_sym; };
+    auto load_raw = [&](uint32_t t) {
+        if (is_full(t)) {
+#pragma unroll
+            for (int g = 0; g < ENC_GROUPS; g++)
+                raw[g] = ld_stream_v4(in_bytes + ((uint64_t)t * ENC_TILE_SYMS + (g * ENC_TEAM + ttid) * 8) * 2);
+        }
+    };
+    uint32_t tile = s_tile[team];
+    load_raw(tile);
+
+    while (tile < ntiles) {
         const uint64_t sym0 = (uint64_t)tile * ENC_TILE_SYMS;
         const uint32_t nsym = (uint32_t)min((uint64_t)ENC_TILE_SYMS, n_sym - sym0);
+        const bool full = is_full(tile);
 
-        // ---- 1. load symbols, gather codes, sum lengths ----
-        uint32_t e[ENC_GROUPS][8];                  // fast path: enc32 entries; long path: symbols
+        // ---- 1. symbols -> table entries, length sums ----
+        uint32_t v[ENC_GROUPS][8];                  // (1 << len) | code, or V_FALLBACK | symbol
         uint32_t glen[ENC_GROUPS];
 #pragma unroll
         for (int g = 0; g < ENC_GROUPS; g++) {
-            const uint32_t s_base = (g * ENC_THREADS + tid) * 8;      // first symbol of this group in the tile
             uint32_t sym[8];
-            if (s_base + 8 <= nsym) {
-                uint4 v = ld_stream_v4(in_bytes + (sym0 + s_base) * 2);
-                sym[0] = v.x & 0xFFFFu; sym[1] = v.x >> 16; sym[2] = v.y & 0xFFFFu; sym[3] = v.y >> 16;
-                sym[4] = v.z & 0xFFFFu; sym[5] = v.z >> 16; sym[6] = v.w & 0xFFFFu; sym[7] = v.w >> 16;
+            if (full) {
+                const uint4 x = raw[g];
+                sym[0] = x.x & 0xFFFFu; sym[1] = x.x >> 16; sym[2] = x.y & 0xFFFFu; sym[3] = x.y >> 16;
+                sym[4] = x.z & 0xFFFFu; sym[5] = x.z >> 16; sym[6] = x.w & 0xFFFFu; sym[7] = x.w >> 16;
             } else {
+                const uint32_t s_base = (g * ENC_TEAM + ttid) * 8;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    uint64_t s = sym0 + s_base + j;
-                    sym[j] = (s_base + j < nsym)
-                                 ? (uint32_t)in_bytes[2 * s] | ((uint32_t)in_bytes[2 * s + 1] << 8)
-                                 : 0x10000u;        // marker: no symbol
-                }
+                for (int j = 0; j < 8; j++) sym[j] = (s_base + j < nsym) ? (uint32_t)in16[sym0 + s_base + j] : 0x10000u;
             }
-            uint32_t L = 0;
+            uint32_t L = 0, zero = 0xFFFFFFFFu;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                if (LONG) {
-                    e[g][j] = sym[j];
-                    L += sym[j] < NSYM ? cb->len[sym[j]] : 0;
-                } else {
-                    uint32_t x = sym[j] < NSYM ? __ldg(&enc32[sym[j]]) : 0u;
-                    e[g][j] = x;
-                    L += x >> 27;
+                const uint32_t f = fold16(sym[j] & 0xFFFFu);
+                uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
+                if (!full && sym[j] > 0xFFFFu) x = 1u;         // no symbol: zero bits
+                v[g][j] = x;
+                zero = min(zero, x);
+                L += 31 - __clz(x | 1u);
+            }
+            if (zero == 0) {                                    // some code is longer than 23 bits: rare
+                L = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (v[g][j] == 0) { v[g][j] = V_FALLBACK | sym[j]; L += cb->len[sym[j]]; }
+                    else L += 31 - __clz(v[g][j]);
                 }
             }
             glen[g] = L;
         }
 
-        // ---- CTA exclusive scan of (glen[0], glen[1]) packed in one 64-bit value ----
-        unsigned long long pk = (unsigned long long)glen[0] | ((unsigned long long)glen[1] << 32);
+        // ---- team exclusive scan of (glen[0], glen[1]) packed in one 64-bit value;
+        //      the claim of the next tile rides on the same barriers ----
+        if (ttid == 0) s_tile[team] = (uint32_t)atomicAdd(&work->counter, 1ull);
+        const unsigned long long pk = (unsigned long long)glen[0] | ((unsigned long long)glen[1] << 32);
         unsigned long long x = pk;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
             if (lane >= o) x += y;
         }
-        if (lane == 31) s_scan[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long s = lane < ENC_THREADS / 32 ? s_scan[lane] : 0ull;
+        if (lane == 31) s_scan[team][twid] = x;
+        team_sync(team);
+        if (twid == 0) {
+            unsigned long long s = lane < ENC_TEAM / 32 ? s_scan[team][lane] : 0ull;
             unsigned long long t = s;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < ENC_TEAM / 32; o <<= 1) {
                 unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
                 if (lane >= o) t += y;
             }
-            if (lane < ENC_THREADS / 32) s_scan[lane] = t - s;
-            if (lane == 31) s_scan[16] = t;         // totals of both groups
+            if (lane < ENC_TEAM / 32) s_scan[team][lane] = t - s;
+            if (lane == ENC_TEAM / 32 - 1) s_scan[team][8] = t;   // totals of both groups
         }
-        __syncthreads();
-        const unsigned long long excl = x - pk + s_scan[wid];
-        const unsigned long long tot = s_scan[16];
+        team_sync(team);
+        const uint32_t next_tile = s_tile[team];
+        load_raw(next_tile);                                    // in flight while this tile is packed
+        const unsigned long long excl = x - pk + s_scan[team][twid];
+        const unsigned long long tot = s_scan[team][8];
         const uint32_t totA = (uint32_t)tot, totB = (uint32_t)(tot >> 32);
         const uint32_t tile_bits = totA + totB;
-        uint32_t off[ENC_GROUPS] = {(uint32_t)excl, totA + (uint32_t)(excl >> 32)};
+        const uint32_t off[ENC_GROUPS] = {(uint32_t)excl, totA + (uint32_t)(excl >> 32)};
 
         // ---- 2. decoupled look-back for the tile's exclusive bit prefix ----
-        if (wid == 0) {
+        if (twid == 0) {
             unsigned long long prefix = 0;
             if (tile == 0) {
                 if (lane == 0) st_release_u64(&desc[0], ((unsigned long long)ST_INCL << 62) | tile_bits);
@@ -172,120 +217,153 @@ encode_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebo
                         if (++spins > SPIN_LIMIT) { if (lane == 0) atomicExch(&work->error, 1ull); break; }
                         continue;
                     }
-                    unsigned long long v = (lane <= first) ? (d & 0x3FFFFFFFFFFFFFFFull) : 0ull;
+                    unsigned long long val = (lane <= first) ? (d & 0x3FFFFFFFFFFFFFFFull) : 0ull;
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                    prefix += v;
+                    for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, o);
+                    prefix += val;
                     if (first < 32) break;
                     look -= 32;
                 }
                 if (lane == 0) st_release_u64(&desc[tile], ((unsigned long long)ST_INCL << 62) | (prefix + tile_bits));
             }
-            if (lane == 0) s_bcast[0] = prefix;
+            if (lane == 0) s_bcast[team] = prefix;
         }
-        // zero the staging buffer while warp 0 looks back
-        for (uint32_t i = tid; i < EncCfg<LONG>::STAGE_WORDS / 4; i += ENC_THREADS)
+        // the first window can be zeroed while warp 0 looks back
+        for (uint32_t i = ttid; i < ENC_WIN / 4; i += ENC_TEAM)
             reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        const unsigned long long gbit = bit0 + s_bcast[0];          // tile's first bit, frame coordinates
+        team_sync(team);
+        const unsigned long long gbit = bit0 + s_bcast[team];       // tile's first bit, frame coordinates
         const unsigned long long gend = gbit + tile_bits;
         const uint32_t phase = (uint32_t)(gbit & 127);
-        const unsigned long long G0 = (gbit - phase) >> 5;          // frame word of staging word 0 (multiple of 4)
-
-        // ---- 3. pack this thread's codes into staging ----
-#pragma unroll
-        for (int g = 0; g < ENC_GROUPS; g++) {
-            uint32_t pos = phase + off[g];
-            uint32_t w = pos >> 5;
-            uint32_t nb = pos & 31;
-            bool shared_first = nb != 0;
-            unsigned long long acc = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (LONG) {
-                    uint32_t s = e[g][j];
-                    if (s < NSYM) {
-                        uint32_t len = cb->len[s];
-                        unsigned long long code = cb->code[s];
-                        if (len > 32) { put_bits(stage, acc, nb, w, shared_first, (uint32_t)(code >> 32), len - 32); len = 32; }
-                        put_bits(stage, acc, nb, w, shared_first, (uint32_t)code, len);
-                    }
-                } else {
-                    put_bits(stage, acc, nb, w, shared_first, e[g][j] & 0x07FFFFFFu, e[g][j] >> 27);
-                }
-            }
-            if (nb) atomicOr(&stage[w], (uint32_t)(acc >> 32));     // tail word shared with the next thread
-        }
-        __syncthreads();
-
-        // ---- 4. seam handling, then copy out ----
-        const unsigned long long first_w = gbit >> 5;               // frame word holding the tile's first bit
-        const unsigned long long end_w = gend >> 5;                 // frame word holding the bit after the tile
+        const unsigned long long G0 = (gbit - phase) >> 5;          // frame word of tile-relative word 0 (multiple of 4)
         const bool last_tile = tile + 1 == ntiles;
-        if (tid == 0) {
-            const bool tail_is_seam = end_w == first_w;             // tiny tile: tail word needs the predecessor's bits
-            if (!tail_is_seam && !last_tile)
-                st_release_u64(&tails[tile], (1ull << 63) | stage[end_w - G0]);
-            uint32_t carry = 0;
-            if (tile == 0) {
-                // preserve the bits of the first byte that precede the start phase
-                uint32_t b = frame[gbit >> 3];
-                uint32_t keep = b & ~(0xFFu >> (gbit & 7));
-                carry = keep << (24 - 8 * (uint32_t)((gbit >> 3) & 3));
-            } else {
-                unsigned long long t;
-                uint32_t spins = 0;
-                while (((t = ld_acquire_u64(&tails[tile - 1])) >> 63) == 0)
-                    if (++spins > SPIN_LIMIT) { atomicExch(&work->error, 2ull); break; }
-                carry = (uint32_t)t;
-            }
-            stage[first_w - G0] |= carry;
-            if (tail_is_seam && !last_tile)
-                st_release_u64(&tails[tile], (1ull << 63) | stage[end_w - G0]);
-        }
-        __syncthreads();
+        // words I own: those whose first bit is mine (tile 0 also owns the word the stream starts in)
+        const unsigned long long own_lo = tile == 0 ? (gbit >> 5) : ((gbit + 31) >> 5);
+        const unsigned long long own_hi = tile_bits ? ((gend - 1) >> 5) : 0;       // valid when tile_bits > 0
+        const bool owns = tile_bits > 0 && own_hi >= own_lo;
+        const uint32_t hi_rel = (uint32_t)(own_hi - G0);
+        const uint32_t npass = owns ? hi_rel / ENC_WIN + 1 : 0;
 
-        // words [first_w, end_w) are complete.  The very first word of the stream is stored
-        // bytewise from the start byte on; the last tile also stores the final partial bytes.
-        const uint32_t n_groups = (uint32_t)((end_w - G0 + 4) >> 2);
-        uint32_t *gw = reinterpret_cast<uint32_t *>(frame);
-        for (uint32_t q = tid; q < n_groups; q += ENC_THREADS) {
-            const unsigned long long w0 = G0 + 4ull * q;
-            uint4 v = reinterpret_cast<const uint4 *>(stage)[q];
-            v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
-            const bool has_stream_head = (tile == 0) && (w0 <= first_w);
-            if (w0 >= first_w && w0 + 4 <= end_w && !has_stream_head) {
-                st_stream_v4(gw + w0, v);
-            } else {
-                uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        for (uint32_t pass = 0; pass < npass; pass++) {
+            const uint32_t wbase = pass * ENC_WIN;
+            if (pass) {
+                team_sync(team);                                    // the previous window has left
+                for (uint32_t i = ttid; i < ENC_WIN / 4; i += ENC_TEAM)
+                    reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+                team_sync(team);
+            }
+
+            // ---- 3. OR this thread's codes into the window ----
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned long long wk = w0 + k;
-                    if (wk < first_w || wk > end_w) continue;
-                    uint32_t b_lo = 0, b_hi = 4;                    // byte range [b_lo, b_hi) of this word to store
-                    if (tile == 0 && wk == first_w) b_lo = (uint32_t)((gbit >> 3) & 3);
-                    if (wk == end_w) {
-                        if (!last_tile) continue;                   // completed by the next tile
-                        b_hi = (uint32_t)(((gend & 31) + 7) >> 3);  // bytes holding payload bits
+            for (int g = 0; g < ENC_GROUPS; g++) {
+                uint32_t pos = phase + off[g];
+                if (((pos + glen[g]) >> 5) < wbase || (pos >> 5) >= wbase + ENC_WIN) continue;   // nothing of mine in this window
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t e = v[g][j];
+                    if (e & V_FALLBACK) {
+                        const uint32_t s = e & 0xFFFFu;
+                        const uint32_t len = cb->len[s];
+                        const unsigned long long code = cb->code[s];
+                        if (len > 32) {
+                            or_code(stage, wbase, pos, (uint32_t)((code << (64 - len)) >> 32), 32);
+                            or_code(stage, wbase, pos + 32, (uint32_t)(code << (64 - len)), len - 32);
+                        } else if (len) {
+                            or_code(stage, wbase, pos, (uint32_t)code << (32 - len), len);
+                        }
+                        pos += len;
+                    } else {
+                        const uint32_t len = 31 - __clz(e);
+                        or_code(stage, wbase, pos, __funnelshift_lc(0u, e, 32 - len), len);   // the leading one falls off
+                        pos += len;
                     }
-                    if (b_lo == 0 && b_hi == 4) gw[wk] = vv[k];
-                    else
-                        for (uint32_t b = b_lo; b < b_hi; b++)
-                            frame[wk * 4 + b] = (uint8_t)(vv[k] >> (8 * b));   // little-endian view of the swapped word
+                }
+            }
+            team_sync(team);
+
+            // ---- 4. the stream head (tile 0) and my last, partial word ----
+            const bool last_pass = pass + 1 == npass;
+            if (ttid == 0) {
+                if (pass == 0 && tile == 0) {
+                    // preserve the bits of the first byte that precede the start phase
+                    const uint32_t b = frame[gbit >> 3];
+                    const uint32_t keep = b & ~(0xFFu >> (gbit & 7));
+                    stage[(gbit >> 5) - G0] |= keep << (24 - 8 * (uint32_t)((gbit >> 3) & 3));
+                }
+                if (last_pass) {
+                    unsigned long long fin = last_tile ? gend : NOT_FINAL;
+                    uint32_t have = (uint32_t)(gend & 31);          // bits of my last word that are mine
+                    if (have && !last_tile) {
+                        // complete the word with the codes of the symbols that follow the tile
+                        uint32_t word = 0;
+                        uint64_t s = sym0 + nsym;
+                        unsigned long long end = gend;
+                        while (have < 32 && s < n_sym) {
+                            uint32_t len;
+                            unsigned long long code;
+                            lookup_slow(p16, p8, cb, in16[s], len, code);
+                            if (len) {
+                                const unsigned long long left = code << (64 - len);        // left aligned
+                                word |= (uint32_t)(left >> 32) >> have;
+                                have += len;
+                                end += len;
+                            }
+                            s++;
+                        }
+                        stage[hi_rel - wbase] |= word;
+                        if (have < 32) fin = end;                   // the input ended inside my word: it is the last one
+                    }
+                    s_final[team] = fin;
+                }
+            }
+            team_sync(team);
+            const unsigned long long fin = last_pass ? s_final[team] : NOT_FINAL;
+
+            // my words of this window leave: 128-bit stores where a whole group is mine, else words / bytes
+            const unsigned long long W0 = G0 + wbase;
+            uint32_t n_groups = ENC_WIN / 4;
+            if (own_hi < W0 + ENC_WIN) n_groups = (uint32_t)((own_hi - W0 + 4) >> 2);
+            uint32_t *gw = reinterpret_cast<uint32_t *>(frame);
+            for (uint32_t q = ttid; q < n_groups; q += ENC_TEAM) {
+                const unsigned long long w0 = W0 + 4ull * q;
+                uint4 o = reinterpret_cast<const uint4 *>(stage)[q];
+                o.x = bswap32(o.x); o.y = bswap32(o.y); o.z = bswap32(o.z); o.w = bswap32(o.w);
+                const bool whole = w0 >= own_lo && w0 + 3 <= own_hi && !(tile == 0 && w0 <= (bit0 >> 5)) &&
+                                   !(fin != NOT_FINAL && w0 + 3 == own_hi);
+                if (whole) {
+                    st_stream_v4(gw + w0, o);
+                } else {
+                    const uint32_t vv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned long long wk = w0 + k;
+                        if (wk < own_lo || wk > own_hi) continue;
+                        uint32_t b_lo = 0, b_hi = 4;                // byte range [b_lo, b_hi) of this word to store
+                        if (wk == (bit0 >> 5)) b_lo = (uint32_t)((bit0 >> 3) & 3);   // bytes before the stream are not ours
+                        if (fin != NOT_FINAL && wk == own_hi) b_hi = (uint32_t)(((fin - 1) >> 3) & 3) + 1;   // bytes holding bits
+                        if (b_lo == 0 && b_hi == 4) gw[wk] = vv[k];
+                        else
+                            for (uint32_t b = b_lo; b < b_hi; b++)
+                                frame[wk * 4 + b] = (uint8_t)(vv[k] >> (8 * b));   // little-endian view of the swapped word
+                    }
                 }
             }
         }
+        team_sync(team);                                            // staging, s_tile, s_final reuse
+        tile = next_tile;
     }
 }
 
-static size_t enc_work_bytes(uint32_t ntiles) { return sizeof(EncWork) + (size_t)ntiles * 16; }
+static size_t enc_work_bytes(uint32_t ntiles) { return sizeof(EncWork) + (size_t)ntiles * 8; }
 
 int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
                   uint64_t start_bit, uint32_t maxlen_hint)
 {
+    (void)maxlen_hint;
     const uint64_t n_sym = n_bytes / 2;
     if (n_sym == 0) return HF_OK;
     if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
+    if ((uintptr_t)d_cb & 15) return set_err(c, HF_ERR_ARG, "hf_encode: codebook must be 16-byte aligned");
     const uint64_t nt64 = (n_sym + ENC_TILE_SYMS - 1) / ENC_TILE_SYMS;
     if (nt64 > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_encode: input too large");
     const uint32_t ntiles = (uint32_t)nt64;
@@ -297,28 +375,17 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     HF_CUDA(c, cudaMemsetAsync(work, 0, enc_work_bytes(ntiles), c->stream));
 
     static bool attr_set = false;
-    const size_t smem_fast = EncCfg<false>::STAGE_WORDS * 4, smem_long = EncCfg<true>::STAGE_WORDS * 4;
     if (!attr_set) {
-        HF_CUDA(c, cudaFuncSetAttribute(encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-        HF_CUDA(c, cudaFuncSetAttribute(encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
+        HF_CUDA(c, cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
         attr_set = true;
     }
     // start_bit may exceed 8: fold whole bytes into the pointer
     d_stream += start_bit >> 3;
     start_bit &= 7;
-    int occ_fast = 0, occ_long = 0;
-    HF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, encode_kernel<false>, ENC_THREADS, smem_fast));
-    HF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, encode_kernel<true>, ENC_THREADS, smem_long));
-    if (maxlen_hint == 0 || maxlen_hint <= ENC32_MAX_LEN) {
-        uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)c->sm_count * (occ_fast > 0 ? occ_fast : 1));
-        HF_PROF(c, "encode_kernel<false>"); encode_kernel<false><<<grid, ENC_THREADS, smem_fast, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
-        HF_LAUNCH_CHECK(c);
-    }
-    if (maxlen_hint == 0 || maxlen_hint > ENC32_MAX_LEN) {
-        uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)c->sm_count * (occ_long > 0 ? occ_long : 1));
-        HF_PROF(c, "encode_kernel<true>"); encode_kernel<true><<<grid, ENC_THREADS, smem_long, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
-        HF_LAUNCH_CHECK(c);
-    }
+    const uint32_t ctas = (ntiles + ENC_NT - 1) / ENC_NT;
+    const uint32_t grid = ctas < (uint32_t)c->sm_count ? ctas : (uint32_t)c->sm_count;
+    HF_PROF(c, "encode_kernel"); encode_kernel<<<grid, ENC_THREADS, ENC_SMEM, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, work, ntiles);
+    HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 

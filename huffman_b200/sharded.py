@@ -11,14 +11,15 @@ Compress
   3. shard payload bits = dot(local hist, len) -> all_gather of one i64 per rank -> the rank's
      global start bit by an exclusive prefix over ranks
   4. the rank packs its chunk at that bit phase; rank 0 also packs the header
-  5. all_gather of every slice's first 32 bytes: the byte shared with the previous slice is
-     OR-merged and the rest kept as read-ahead (`halo`) for the decoder
-Decompress
-  1. each rank walks its byte range from a GUESSED first bit (only rank 0 knows the true one: the
-     format has no offset index) and self-synchronises            -> all_gather(next-bit, count)
-  2. a rank whose guess differs from the previous rank's true overflow repairs its head
-     (repeat while anything changed: at most world-1 rounds, 1 in practice)
-  3. the counts give every rank's output offset; each rank emits its symbols
+  5. all_gather of every slice's first 32 bytes and last byte: seam bytes are OR-merged and the
+     bytes that follow a slice are kept behind it as read-ahead (`halo`) for the decoder
+Decompress (the format has no offset index: only rank 0 knows where its first code word starts)
+  1. each rank finds, by self-synchronising over the last 16 KiB of its byte range, where the first
+     code word AFTER its range starts                              -> all_gather(overflow, range bits)
+  2. each rank decodes its range from its predecessor's overflow; the overflow it really ends with
+     must confirm the speculated one                               -> all_gather(overflow, count, flags)
+  3. the counts give every rank's output offset.  A stream that fails the check (it does not
+     self-synchronise) is gathered and decoded on rank 0 by the exact kernels.
 
 The kernels are reached through a `stages` object (huffman_b200.codec.Codec in production: CUDA
 only, no CPU fallback); the CPU gloo tests plug in an oracle-backed stand-in to exercise this
@@ -211,28 +212,50 @@ class ShardedCodec:
             if mine:
                 st.decode(sl.buf, int(info.payload_start_bit), mine, table, out)
             return out[:2 * mine], 0 if self.rank == 0 else n_total & ~1, n_total
-        # 1. walk my byte range from a guessed first bit (rank 0 knows the true one)
-        first_bit, exact = (int(info.payload_start_bit), True) if self.rank == 0 else (0, False)
-        state = st.decode_scan(sl.buf, sl.range_bytes, HALO, first_bit, exact, table)
-        res = self._all_gather(state.result()).cpu()          # [world, 2]: next_bit past my range, n_symbols
-        for _ in range(self.world - 1):
-            changed = torch.zeros(1, dtype=torch.int64, device=sl.buf.device)
-            if self.rank > 0:
-                want = int(res[self.rank - 1, 0])             # the previous rank's overflow = my true first bit
-                if want != state.first_bit:
-                    st.decode_rebase(state, want)
-                    changed += 1
-            self._all_reduce(changed)
-            if int(changed.item()) == 0:
-                break
-            res = self._all_gather(state.result()).cpu()
-        counts = [int(c) for c in res[:, 1]]
+        dev = sl.buf.device
+        my_bits = sl.range_bytes * 8
+        # 1. where does the first code word after my range start?  (speculative: self-synchronisation over
+        #    the last 16 KiB of the range); every rank needs its predecessor's answer
+        probe = st.range_overflow(sl.buf, sl.range_bytes, HALO, table) if sl.range_bytes else \
+            torch.zeros(4, dtype=torch.int64, device=dev)
+        mine = torch.stack([probe[1], torch.tensor(my_bits, dtype=torch.int64, device=dev)])
+        got = self._all_gather(mine).cpu()
+        first = [int(info.payload_start_bit)]              # first[r]: rank r's first code word, bits into its range
+        over = []
+        for r in range(self.world):
+            rb = int(got[r, 1])
+            e = first[r] - rb if first[r] >= rb else int(got[r, 0])      # a range no code word starts in passes it on
+            over.append(e)
+            first.append(e)
+        # 2. decode my range from that bit; the real overflow must confirm the speculated one
         n_sym_total = n_total // 2
+        cap = sl.n_total // (2 * self.world) + (1 << 16) if out is None else out.numel() // 2
+        for attempt in range(2):
+            if out is None or out.numel() < 2 * cap:
+                out = torch.empty(2 * cap, dtype=torch.uint8, device=dev)
+            if first[self.rank] < my_bits:
+                res = st.decode_range(sl.buf, sl.range_bytes, HALO, first[self.rank], table, out).clone()
+            else:
+                res = torch.tensor([0, over[self.rank], 0, 0], dtype=torch.int64, device=dev)
+            allres = self._all_gather(res).cpu()
+            if not any(int(f) & 8 for f in allres[:, 3]):
+                break
+            cap = int(allres[self.rank, 2]) + 16           # my output buffer was too small: the count is known now
+            out = None
+        bad = any(int(allres[r, 3]) != 0 or int(allres[r, 1]) != over[r] for r in range(self.world))
+        if bad:
+            return self._decompress_on_rank0(sl, n_total)
+        counts = [int(c) for c in allres[:, 2]]
         offs = [0]
         for c in counts[:-1]:
             offs.append(offs[-1] + c)
-        mine = max(0, min(counts[self.rank], n_sym_total - offs[self.rank]))
-        if out is None or out.numel() < 2 * mine:
-            out = torch.empty(max(2 * mine, 2), dtype=torch.uint8, device=sl.buf.device)
-        st.decode_emit(state, mine, out)
-        return out[:2 * mine], 2 * min(offs[self.rank], n_sym_total), n_total
+        mine_n = max(0, min(counts[self.rank], n_sym_total - offs[self.rank]))
+        return out[:2 * mine_n], 2 * min(offs[self.rank], n_sym_total), n_total
+
+    def _decompress_on_rank0(self, sl, n_total):
+        """streams that do not self-synchronise (SURVEY.md 7 "adversarial streams"): no rank can find its
+        start by itself, so the slices go to rank 0, which decodes the whole image with the exact kernels"""
+        image = self.gather_image(sl)
+        if self.rank == 0:
+            return self.st.decompress(image), 0, n_total
+        return torch.empty(0, dtype=torch.uint8, device=sl.buf.device), n_total & ~1, n_total

@@ -161,6 +161,30 @@ int hf_decode_table_from_codebook(hf_ctx *ctx, const void *d_codebook, void *d_d
 int hf_decode(hf_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
               uint64_t n_symbols, const void *d_decode_table, uint8_t *d_out);
 
+/* One rank's BYTE RANGE of a stream sharded over several GPUs (the reference is
+ * single-GPU and its format has no offset index, D:259-284).  d_range points at the first byte of
+ * the range; halo_bytes (>= 16) after it are readable: the following bytes of the same stream,
+ * zeros past its end.
+ *   hf_range_overflow: where does the first code word AFTER the range start?  Found speculatively
+ *     by self-synchronising over the last 16 KiB of the range; d_result[1] = bits past the range
+ *     end.  The ranks all-gather these values: each is the next rank's first bit.
+ *   hf_decode_range: decodes the code words that start inside the range, the first one first_bit
+ *     bits into it, into d_out (at most out_symbols).  d_result (device u64[4]): [1] overflow of
+ *     the last code word past the range end (must equal what hf_range_overflow predicted),
+ *     [2] symbols decoded, [3] flags: 1 the stream did not self-synchronise within a 16 KiB
+ *     chunk, 4 invalid code, 8 out_symbols too small, 16 internal.  Any flag means d_out must not
+ *     be used.  Both calls are asynchronous. */
+int hf_range_overflow(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
+                      const void *d_decode_table, uint64_t *d_result);
+int hf_decode_range(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
+                    uint64_t first_bit, const void *d_decode_table, uint8_t *d_out, uint64_t out_symbols,
+                    uint64_t *d_result);
+
+/* hf_decode / hf_decompress normally run the single-pass decoder and fall back (on the device) to
+ * the exact multi-pass kernels for streams that do not self-synchronise; exact_only = 1 forces the
+ * exact kernels (used by the tests to cover both). */
+int hf_set_decode_mode(hf_ctx *ctx, int exact_only);
+
 /* whole `extract` data path on device buffers.  Synchronises. */
 int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8_t *d_out,
                   uint64_t capacity, uint64_t *h_out_bytes);

@@ -18,35 +18,24 @@ class FakeCodebook:
         self.hist = hist
 
 
-class FakeScan:
-    def __init__(self, buf, range_bytes, halo, first_bit, table):
-        self.buf, self.range_bytes, self.halo, self.first_bit, self.table = buf, range_bytes, halo, first_bit, table
-        self.walk()
-
-    def walk(self):
-        bits = np.unpackbits(self.buf[: self.range_bytes + self.halo].numpy())
-        end = self.range_bytes * 8
-        pos, syms = self.first_bit, []
-        inv, maxlen = self.table
-        while pos < end:
-            for ln in range(1, maxlen + 1):
-                if pos + ln > bits.size:
-                    ln = None
-                    break
-                key = (ln, int("".join(map(str, bits[pos:pos + ln])), 2))
-                if key in inv:
-                    syms.append(inv[key])
-                    pos += ln
-                    break
-            else:
-                ln = None
-            if ln is None:                       # no code word here (garbage from a wrong guess): step one bit
-                pos += 1
-        self.syms = syms
-        self.next_bit = pos - end if self.range_bytes else self.first_bit
-
-    def result(self):
-        return torch.tensor([self.next_bit, len(self.syms)], dtype=torch.int64)
+def _walk(buf, range_bytes, halo, start_bit, table, from_bit=0):
+    """decode code words from start_bit while they START before the range end; returns (symbols, overflow)"""
+    bits = np.unpackbits(buf[: range_bytes + halo].numpy())
+    end = range_bytes * 8
+    pos, syms = max(start_bit, from_bit), []
+    inv, maxlen = table
+    while pos < end:
+        ln = None
+        for cand in range(1, maxlen + 1):
+            if pos + cand > bits.size:
+                break
+            key = (cand, int("".join(map(str, bits[pos:pos + cand])), 2))
+            if key in inv:
+                ln = cand
+                syms.append(inv[key])
+                break
+        pos += ln if ln else 1                   # no code word here (garbage from a wrong guess): step one bit
+    return syms, pos - end
 
 
 class FakeStages:
@@ -138,13 +127,18 @@ class FakeStages:
         sym = next(iter(inv.values()))
         out[: 2 * n_symbols] = torch.from_numpy(np.full(n_symbols, sym, np.uint16).view(np.uint8).copy())
 
-    def decode_scan(self, buf, range_bytes, halo_bytes, first_bit, exact, table):
-        return FakeScan(buf, range_bytes, halo_bytes, first_bit, table)
+    def range_overflow(self, buf, range_bytes, halo_bytes, table, result=None):
+        # speculative: start at bit 0 of the last 16 KiB of the range, like the kernel's tail chunk
+        start = max(0, range_bytes * 8 - 16384 * 8)
+        _, over = _walk(buf, range_bytes, halo_bytes, start, table)
+        return torch.tensor([0, over, 0, 0], dtype=torch.int64)
 
-    def decode_rebase(self, state, true_first_bit):
-        state.first_bit = true_first_bit
-        state.walk()
+    def decode_range(self, buf, range_bytes, halo_bytes, first_bit, table, out, result=None):
+        syms, over = _walk(buf, range_bytes, halo_bytes, first_bit, table)
+        flags = 8 if len(syms) > out.numel() // 2 else 0
+        if not flags:
+            out[: 2 * len(syms)] = torch.from_numpy(np.array(syms, dtype=np.uint16).view(np.uint8).copy())
+        return torch.tensor([0, over, len(syms), flags], dtype=torch.int64)
 
-    def decode_emit(self, state, n_symbols, out):
-        s = np.array(state.syms[:n_symbols], dtype=np.uint16)
-        out[: 2 * n_symbols] = torch.from_numpy(s.view(np.uint8).copy())
+    def decompress(self, image):
+        return torch.from_numpy(O.decompress(image.numpy()))

@@ -192,6 +192,19 @@ def test_decompress_oracle_images(codec, oracle, name):
     assert np.array_equal(got.cpu().numpy(), data)
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_decompress_exact_path_only(codec, oracle, name):
+    """the exact multi-pass decoder alone (normally only the fallback of the single-pass one)"""
+    data = CASES[name]
+    image = oracle.compress(data)
+    codec.set_decode_mode(True)
+    try:
+        got = codec.decompress(dev(image))
+    finally:
+        codec.set_decode_mode(False)
+    assert np.array_equal(got.cpu().numpy(), data)
+
+
 def test_round_trip_fixtures(codec, romeo, jpeg):
     for data in (romeo, jpeg, synth.pdf15m()):
         d = dev(data)
