@@ -54,6 +54,7 @@ _SIGS = {
     "hf_profile_enable": (ctypes.c_int, [_P, ctypes.c_int]),
     "hf_profile_read": (ctypes.c_int, [_P, ctypes.POINTER(KernelTime), ctypes.c_uint32,
                                        ctypes.POINTER(ctypes.c_uint32)]),
+    "hf_debug_read_ws": (ctypes.c_int, [_P, _U64, _P, _U64]),
     "hf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t]),
     "hf_host_free": (ctypes.c_int, [_P]),
     "hf_codebook_bytes": (ctypes.c_size_t, []),

@@ -203,6 +203,17 @@ int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *
     return HF_OK;
 }
 
+// development aid: copies `bytes` of the context's workspace at byte offset `off` to the host (timing builds)
+int hf_debug_read_ws(hf_ctx *ctx, uint64_t off, void *h_dst, uint64_t bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!c->ws || off + bytes > c->ws_bytes) return set_err(c, HF_ERR_ARG, "hf_debug_read_ws: out of range");
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    HF_CUDA(c, cudaMemcpy(h_dst, (uint8_t *)c->ws + off, bytes, cudaMemcpyDeviceToHost));
+    return HF_OK;
+}
+
 int hf_host_alloc(void **h_ptr, size_t bytes)
 {
     if (!h_ptr) return HF_ERR_ARG;

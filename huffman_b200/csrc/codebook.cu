@@ -293,6 +293,7 @@ __global__ void cb_codes_kernel(const unsigned long long *__restrict__ hist, CbW
         const uint32_t fsym = sym ^ (sym >> 8);                 // the encoder's bank-spreading index (encode.cu fold16)
         cb->p16[fsym] = (uint16_t)v24;
         cb->p8[fsym] = (uint8_t)(v24 >> 16);
+        cb->lenf[fsym] = (uint8_t)len;
         w->entry_bits[k] = 24 + len;
         tb = 24 + len;
         pb = hist[sym] * len;

@@ -38,6 +38,7 @@ struct Codebook {
     // aligned (copied to shared memory with 128-bit loads)
     alignas(16) uint16_t p16[NSYM];
     uint8_t p8[NSYM];
+    uint8_t lenf[NSYM];        // code length by folded symbol (enc_count_kernel's shared-memory plane)
 };
 static_assert(offsetof(Codebook, p16) % 16 == 0, "encoder planes must be 16-byte aligned");
 static_assert(offsetof(Codebook, p8) == offsetof(Codebook, p16) + NSYM * 2, "encoder planes must be contiguous");

@@ -91,6 +91,10 @@ typedef struct {
 int hf_profile_enable(hf_ctx *ctx, int on);
 int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *n_out);
 
+/* development aid (phase-timing builds): synchronises and copies a piece of the context's
+ * device workspace to the host */
+int hf_debug_read_ws(hf_ctx *ctx, uint64_t off, void *h_dst, uint64_t bytes);
+
 /* pinned host buffers for the host-facing calls (C:343 uses cudaHostAlloc) */
 int hf_host_alloc(void **h_ptr, size_t bytes);
 int hf_host_free(void *h_ptr);
