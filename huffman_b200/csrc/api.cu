@@ -105,6 +105,7 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     c->sm_count = prop.multiProcessorCount;
     c->stream = (cudaStream_t)stream;                   // NULL = the legacy default stream, as the reference uses
     c->own_stream = false;
+    c->decode_exact_only = true;                        // see hf_set_decode_mode
     bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scratch, 4096) == cudaSuccess;

@@ -40,6 +40,7 @@ constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits =
 constexpr uint32_t CHUNK_WORDS = CHUNK_BITS / 32;               // 4096
 constexpr uint32_t CHUNK_PAD_WORDS = 8;                         // look-ahead past the chunk
 constexpr uint32_t WIN_SYMS = 16384;                            // output staging window (symbols)
+constexpr uint32_t SW_PADDED = (smem_words_padded(CHUNK_WORDS + CHUNK_PAD_WORDS) + 3) & ~3u;   // staged chunk, padded layout
 
 // result flags of the single-pass decoder (decode_fast.cu) that send the job to the exact kernels below
 constexpr unsigned long long DF_GATE_MASK = 1 | 2 | 4 | 16;
@@ -338,8 +339,8 @@ __device__ __forceinline__ void stage_chunk(uint32_t *sw, const uint8_t *frame, 
         unsigned long long byte = (v0 + i) * 16ull;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (byte < frame_bytes) v = ld_stream_v4(frame + byte);      // same 16-byte block as a valid byte
-        v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
-        reinterpret_cast<uint4 *>(sw)[i] = v;
+        uint32_t *dst = sw + smem_word_index(4 * i);        // the four words share one pad group
+        dst[0] = bswap32(v.x); dst[1] = bswap32(v.y); dst[2] = bswap32(v.z); dst[3] = bswap32(v.w);
     }
 }
 
@@ -368,13 +369,58 @@ __device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t
     end = pos - SUB_BITS;
 }
 
+// Walks the code words of the subsequence at staged bit `sub0` from offset `from` up to `lim`, recording
+// every boundary in a 256-bit mask.  HIT: stop at the first position the OLD walk (mask on entry) also
+// visited and splice the old walk's remainder behind the new prefix — a re-synchronisation costs only
+// the few code words it takes to meet the old walk, wherever in the subsequence that happens.
+template <bool HIT>
+__device__ __forceinline__ bool walk_sub(const TabView &T, const uint32_t *sw, uint32_t sub0, uint32_t from, uint32_t lim,
+                                         unsigned long long (&mask)[4], uint32_t &cnt, uint32_t &end, uint32_t &bad)
+{
+    unsigned long long nm[4] = {0, 0, 0, 0};
+    uint32_t pos = from, k = 0;
+    bool hit = false;
+#pragma unroll
+    for (uint32_t s = 0; s < 4; s++) {
+        const uint32_t seg_end = min(lim, (s + 1) * 64);
+        const unsigned long long om = mask[s];
+        unsigned long long m = 0;
+        while (!hit && pos < seg_end) {
+            if (HIT && ((om >> (pos & 63)) & 1ull)) { hit = true; break; }
+            const uint32_t len = decode_at(T, sw, sub0 + pos, bad) & 0x7Fu;
+            m |= 1ull << (pos & 63);
+            k++;
+            pos += len;
+        }
+        nm[s] = m;
+    }
+    if (HIT && hit) {
+        const uint32_t hs = pos >> 6;
+        const unsigned long long keep = ~0ull << (pos & 63);        // old boundaries at or after the meeting point
+        uint32_t c = k;
+#pragma unroll
+        for (uint32_t s = 0; s < 4; s++) {
+            const unsigned long long old = s < hs ? 0ull : (s == hs ? (mask[s] & keep) : mask[s]);
+            c += __popcll(old);
+            mask[s] = nm[s] | old;
+        }
+        cnt = c;                                                     // `end` is the old walk's
+    } else {
+#pragma unroll
+        for (uint32_t s = 0; s < 4; s++) mask[s] = nm[s];
+        cnt = k;
+        end = pos - lim;
+    }
+    return hit;
+}
+
 __global__ void __launch_bounds__(DEC_THREADS)
 dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                 const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                 const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;        // the single-pass decoder succeeded
-    __shared__ __align__(16) uint32_t sw[CHUNK_WORDS + CHUNK_PAD_WORDS];
+    __shared__ __align__(16) uint32_t sw[SW_PADDED];
     __shared__ uint32_t st1[1u << K1];
     __shared__ uint32_t s_end[DEC_THREADS];
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
@@ -386,52 +432,28 @@ dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byte
     __syncthreads();
 
     TabView T{st1, tab->t2, tab->longs, tab->n_long};
-    SmemFetch f{sw};
     const uint32_t g = tab->len_gcd;
     const uint32_t sub_bit0 = tid * SUB_BITS;
     const unsigned long long X = c * CHUNK_BITS + sub_bit0;
     const bool fixed = (c == 0 && tid == 0);            // holds the first payload bit: exact start
     uint32_t p = fixed ? (uint32_t)F0 : spec_start(X, F0, g);
-    uint32_t end, cnt_hi, bad = 0;
-    unsigned long long mask;
-    sub_decode_count(T, f, sub_bit0, p, end, cnt_hi, mask, bad);
-    uint32_t cnt = __popcll(mask) + cnt_hi;
+    uint32_t end = 0, cnt = 0, bad = 0;
+    unsigned long long mask[4] = {0, 0, 0, 0};
+    if (p < SUB_BITS) walk_sub<false>(T, sw, sub_bit0, p, SUB_BITS, mask, cnt, end, bad);
+    else end = p - SUB_BITS;
 
     for (uint32_t it = 0; it < DEC_THREADS + 1; it++) {
         s_end[tid] = end;
         __syncthreads();
         int changed = 0;
         if (tid > 0 && !fixed) {
-            uint32_t q = s_end[tid - 1];
+            const uint32_t q = s_end[tid - 1];
             if (q != p) {
                 // re-synchronise: decode from q until a boundary the recorded walk also visited
-                BitReader<SmemFetch> r{f};
-                r.init(sub_bit0 + q);
-                uint32_t pos = q, k = 0;
-                unsigned long long nmask = 0;
-                bool hit = false;
-                while (pos < 64) {
-                    if ((mask >> pos) & 1ull) { hit = true; break; }
-                    uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
-                    nmask |= 1ull << pos;
-                    pos += len; k++;
-                    r.skip(len);
-                }
-                if (hit) {
-                    cnt = k + __popcll(mask >> pos) + cnt_hi;
-                    mask = nmask | ((mask >> pos) << pos);
-                } else {
-                    uint32_t nhi = 0;
-                    while (pos < SUB_BITS) {
-                        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
-                        nhi++;
-                        pos += len;
-                        r.skip(len);
-                    }
-                    uint32_t nend = pos - SUB_BITS;
-                    changed = nend != end;
-                    end = nend; mask = nmask; cnt_hi = nhi; cnt = k + nhi;
-                }
+                const uint32_t old_end = end;
+                if (q < SUB_BITS) walk_sub<true>(T, sw, sub_bit0, q, SUB_BITS, mask, cnt, end, bad);
+                else { cnt = 0; end = q - SUB_BITS; mask[0] = mask[1] = mask[2] = mask[3] = 0; }
+                changed = end != old_end;
                 p = q;
             }
         }
@@ -552,7 +574,7 @@ dec_write_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     if (gate && !(*gate & DF_GATE_MASK)) return;
     extern __shared__ __align__(16) uint32_t dyn_smem[];
     uint32_t *sw = dyn_smem;                                        // CHUNK_WORDS + CHUNK_PAD_WORDS
-    uint32_t *st1 = sw + CHUNK_WORDS + CHUNK_PAD_WORDS;             // 2^K1
+    uint32_t *st1 = sw + SW_PADDED;                                 // 2^K1
     uint16_t *sout = reinterpret_cast<uint16_t *>(st1 + (1u << K1)); // WIN_SYMS + 8
     __shared__ uint32_t s_w[33];
     if (tab->single_sym) return;
@@ -699,7 +721,7 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
     }
     HF_PROF(c, "dec_scan_kernel"); dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch, gate);
     HF_LAUNCH_CHECK(c);
-    const size_t wsmem = (CHUNK_WORDS + CHUNK_PAD_WORDS + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
+    const size_t wsmem = (SW_PADDED + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
     static bool wattr = false;
     if (!wattr) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));

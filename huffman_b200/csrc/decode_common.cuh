@@ -10,9 +10,13 @@ constexpr uint32_t E_LIST = 0x80000000u;                           // level-2 sl
 
 // -----------------------------------------------------------------------------------
 // bit access.  Fetch functors return big-endian 32-bit word i of some bit string.
+// The chunk's words live in shared memory with one pad word after every 8 (a subsequence is 8 words):
+// lane t reading word j of ITS subsequence hits bank (9t + j) % 32, so the lanes of a warp do not collide.
+__device__ __forceinline__ uint32_t smem_word_index(uint32_t i) { return i + (i >> 3); }
+constexpr uint32_t smem_words_padded(uint32_t n) { return n + (n >> 3) + 1; }
 struct SmemFetch {
     const uint32_t *w;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return w[i]; }
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return w[smem_word_index(i)]; }
 };
 struct GlobalFetch {                    // frame words straight from global memory, zero past the end
     const uint8_t *frame;
@@ -66,12 +70,43 @@ __device__ __forceinline__ unsigned long long peek64(const F &f, uint32_t bitpos
     return (hi << sh) | ((unsigned long long)f(i + 2) >> (32 - sh));
 }
 
+// 32 bits of the staged chunk starting at bit `b` (stateless: two loads and a funnel shift, no refill branch)
+__device__ __forceinline__ uint32_t smem_window32(const uint32_t *sw, uint32_t b)
+{
+    const uint32_t i = b >> 5;
+    return __funnelshift_l(sw[smem_word_index(i + 1)], sw[smem_word_index(i)], b & 31);
+}
+
 struct TabView {
     const uint32_t *t1;                 // shared (kernels A, C) or global (kernel B)
     const uint32_t *t2;
     const LongCode *longs;
     uint32_t n_long;
 };
+
+// one code word at bit `b` of the staged chunk; returns (sym << 8) | len, len >= 1.  K1 + sub bits <= 24 <= 32.
+__device__ __forceinline__ uint32_t decode_at(const TabView &T, const uint32_t *sw, uint32_t b, uint32_t &bad)
+{
+    const uint32_t win = smem_window32(sw, b);
+    uint32_t e = T.t1[win >> (32 - K1)];
+    if (e & E_SUB) {
+        const uint32_t sb = e & 31u;
+        const uint32_t idx2 = (win << K1) >> (32 - sb);
+        e = __ldg(&T.t2[(e >> 8) + idx2]);
+        if (e & E_LIST) {               // longer than K1 + sub bits: walk the slot's list of long codes
+            const unsigned long long w64 = peek64(SmemFetch{sw}, b);
+            uint32_t cur = e;
+            e = 0;
+            while (cur & E_LIST) {
+                const LongCode lc = T.longs[(cur >> 8) & 0xFFFFu];
+                if (((w64 ^ lc.code_left) >> (64 - (lc.leaf & 0x7Fu))) == 0) { e = lc.leaf; break; }
+                cur = lc.next;
+            }
+        }
+    }
+    if (e == 0) { bad = 1; e = 1; }     // hole in the code: flag it, step one bit so the walk ends
+    return e;
+}
 
 // one code word at the reader's position; returns (sym << 8) | len, len >= 1
 template <typename F>

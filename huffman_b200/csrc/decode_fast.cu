@@ -46,7 +46,8 @@ constexpr uint32_t DF_SPIN_LIMIT = 1u << 26;
 constexpr uint32_t DF_ST_INVALID = 0, DF_ST_E = 1, DF_ST_AGG = 2, DF_ST_INCL = 3;
 constexpr unsigned long long DF_VAL_MASK = (1ull << 55) - 1;
 
-constexpr size_t DF_SMEM = (1u << K1) * 4 + DF_BITS_WORDS * 4 + DF_THREADS * DF_SLOT * 2 + 8192 * 2;
+constexpr uint32_t DF_SW_PADDED = (smem_words_padded(DF_BITS_WORDS) + 3) & ~3u;
+constexpr size_t DF_SMEM = (1u << K1) * 4 + DF_SW_PADDED * 4 + DF_THREADS * DF_SLOT * 2 + 8192 * 2;
 
 // flags in result[3]
 constexpr unsigned long long DF_F_MISMATCH = 1, DF_F_BAD = 4, DF_F_CAPACITY = 8, DF_F_SPIN = 16;
@@ -129,7 +130,7 @@ dec_fast_kernel(const DfParams P)
     extern __shared__ __align__(16) uint32_t df_smem[];
     uint32_t *st1 = df_smem;                                    // 2^K1
     uint32_t *sw = st1 + (1u << K1);                            // DF_BITS_WORDS
-    uint16_t *slots = reinterpret_cast<uint16_t *>(sw + DF_BITS_WORDS);
+    uint16_t *slots = reinterpret_cast<uint16_t *>(sw + DF_SW_PADDED);
     uint16_t *sout = slots + DF_THREADS * DF_SLOT;              // 8192 staging symbols (16-byte aligned: see DF_SLOT)
     __shared__ uint32_t s_end[DF_THREADS];
     __shared__ uint32_t s_w[34];
@@ -165,8 +166,8 @@ dec_fast_kernel(const DfParams P)
             const long long b = byte0 + 16ll * i;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (b < P.hi_valid) v = ld_stream_v4(P.frame + b);
-            v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
-            reinterpret_cast<uint4 *>(sw)[i] = v;
+            uint32_t *dst = sw + smem_word_index(4 * i);
+            dst[0] = bswap32(v.x); dst[1] = bswap32(v.y); dst[2] = bswap32(v.z); dst[3] = bswap32(v.w);
         }
 
         // ---- 1. speculative decode of my subsequence ----
