@@ -421,13 +421,13 @@ int hf_set_decode_mode(hf_ctx *ctx, int exact_only)
     return HF_OK;
 }
 
-// flags written by the decode kernels (decode.cu: DecWork.flags) sit at ws + 8 MiB
+// what the decode kernels report (decode.cu: DecWork = result[4], flags[4]) sits at ws + 8 MiB
 static int check_decode_flags(Ctx *c)
 {
     unsigned long long *h = reinterpret_cast<unsigned long long *>((uint8_t *)c->h_scratch + 3072);
-    HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + (8u << 20), 32, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + (8u << 20), 64, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (h[1]) return set_err(c, HF_ERR_FORMAT, "hf_decode: the payload holds bits that are no code word");
+    if (h[4 + 1]) return set_err(c, HF_ERR_FORMAT, "hf_decode: the payload holds bits that are no code word");
     return HF_OK;
 }
 

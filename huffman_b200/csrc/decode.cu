@@ -46,6 +46,7 @@ constexpr uint32_t SW_PADDED = (smem_words_padded(CHUNK_WORDS + CHUNK_PAD_WORDS)
 constexpr unsigned long long DF_GATE_MASK = 1 | 2 | 4 | 16;
 
 struct DecWork {
+    unsigned long long result[4];       // [1] overflow of the last code word past the range end, [2] symbols in the range
     unsigned long long flags[4];        // [0] any chunk failed to sync, [1] invalid code met, [2] table error
     // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32, chunkE2[nch] u32 (0xFFFFFFFF = unchanged),
     //              info[nch * DEC_THREADS] u16
@@ -346,27 +347,37 @@ __device__ __forceinline__ void stage_chunk(uint32_t *sw, const uint8_t *frame, 
 
 // full decode of one subsequence from offset p: overflow, count and the boundary mask of the first 64 bits
 template <typename F>
-__device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t sub_bit0, uint32_t p,
+__device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t sub_bit0, uint32_t p, uint32_t lim,
                                                  uint32_t &end, uint32_t &cnt_hi, unsigned long long &mask,
                                                  uint32_t &bad)
 {
+    mask = 0; cnt_hi = 0;
+    if (p >= lim) { end = p - lim; return; }
     BitReader<F> r{f};
     r.init(sub_bit0 + p);
     uint32_t pos = p;
-    mask = 0; cnt_hi = 0;
-    while (pos < 64) {
+    while (pos < min(64u, lim)) {
         uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
         mask |= 1ull << pos;
         pos += len;
         r.skip(len);
     }
-    while (pos < SUB_BITS) {
+    while (pos < lim) {
         uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
         cnt_hi++;
         pos += len;
         r.skip(len);
     }
-    end = pos - SUB_BITS;
+    end = pos - lim;
+}
+
+// bits of subsequence t of chunk c that lie before the end of the range (0 .. SUB_BITS)
+__device__ __forceinline__ uint32_t sub_limit(unsigned long long c, uint32_t t, unsigned long long range_end_bit)
+{
+    const unsigned long long x = c * CHUNK_BITS + (unsigned long long)t * SUB_BITS;
+    if (x >= range_end_bit) return 0u;
+    const unsigned long long room = range_end_bit - x;
+    return room >= SUB_BITS ? SUB_BITS : (uint32_t)room;
 }
 
 // Walks the code words of the subsequence at staged bit `sub0` from offset `from` up to `lim`, recording
@@ -416,8 +427,8 @@ __device__ __forceinline__ bool walk_sub(const TabView &T, const uint32_t *sw, u
 
 __global__ void __launch_bounds__(DEC_THREADS)
 dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
-                const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                const unsigned long long *gate)
+                unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                unsigned long long nch, unsigned long long c0, uint32_t speculative, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;        // the single-pass decoder succeeded
     __shared__ __align__(16) uint32_t sw[SW_PADDED];
@@ -426,33 +437,36 @@ dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byte
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x;
-    const unsigned long long c = blockIdx.x;
+    const unsigned long long c = c0 + blockIdx.x;
     for (uint32_t i = tid; i < (1u << K1); i += DEC_THREADS) st1[i] = tab->t1[i];
     stage_chunk(sw, frame, frame_bytes, c);
     __syncthreads();
 
     TabView T{st1, tab->t2, tab->longs, tab->n_long};
-    const uint32_t g = tab->len_gcd;
+    const uint32_t g = speculative ? 1u : tab->len_gcd;
     const uint32_t sub_bit0 = tid * SUB_BITS;
     const unsigned long long X = c * CHUNK_BITS + sub_bit0;
-    const bool fixed = (c == 0 && tid == 0);            // holds the first payload bit: exact start
-    uint32_t p = fixed ? (uint32_t)F0 : spec_start(X, F0, g);
+    const uint32_t lim = sub_limit(c, tid, range_end_bit);      // code words starting at or after the range end are not ours
+    const bool fixed = (c == 0 && tid == 0 && !speculative);    // holds the first payload bit: exact start
+    uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
     uint32_t end = 0, cnt = 0, bad = 0;
     unsigned long long mask[4] = {0, 0, 0, 0};
-    if (p < SUB_BITS) walk_sub<false>(T, sw, sub_bit0, p, SUB_BITS, mask, cnt, end, bad);
-    else end = p - SUB_BITS;
+    if (lim) {
+        if (p < lim) walk_sub<false>(T, sw, sub_bit0, p, lim, mask, cnt, end, bad);
+        else end = p - lim;
+    }
 
     for (uint32_t it = 0; it < DEC_THREADS + 1; it++) {
         s_end[tid] = end;
         __syncthreads();
         int changed = 0;
-        if (tid > 0 && !fixed) {
+        if (tid > 0 && !fixed && lim) {
             const uint32_t q = s_end[tid - 1];
             if (q != p) {
                 // re-synchronise: decode from q until a boundary the recorded walk also visited
                 const uint32_t old_end = end;
-                if (q < SUB_BITS) walk_sub<true>(T, sw, sub_bit0, q, SUB_BITS, mask, cnt, end, bad);
-                else { cnt = 0; end = q - SUB_BITS; mask[0] = mask[1] = mask[2] = mask[3] = 0; }
+                if (q < lim) walk_sub<true>(T, sw, sub_bit0, q, lim, mask, cnt, end, bad);
+                else { cnt = 0; end = q - lim; mask[0] = mask[1] = mask[2] = mask[3] = 0; }
                 changed = end != old_end;
                 p = q;
             }
@@ -473,26 +487,35 @@ dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byte
         L.chunkE2[c] = 0xFFFFFFFFu;
     }
     if (tid == DEC_THREADS - 1) L.chunkE[c] = end;
+    // the thread whose subsequence holds the end of the range reports the overflow past it
+    if (lim && sub_limit(c, tid + 1, range_end_bit) == 0) work->result[1] = end;
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
 // repairs chunk c from the true start `s` (frame offset inside the chunk's subsequence 0).
 // Returns true when the walk re-joined the recorded chain before the chunk ended.
 __device__ bool fix_chunk(const TabView &T, const uint8_t *frame, unsigned long long frame_bytes,
-                          DecLayout &L, unsigned long long c, uint32_t s, uint32_t &bad)
+                          unsigned long long range_end_bit, DecWork *work, DecLayout &L, unsigned long long c, uint32_t s,
+                          uint32_t &bad)
 {
     uint16_t *info = L.info + c * DEC_THREADS;
     GlobalFetch f{frame, frame_bytes, c * CHUNK_WORDS};
     uint32_t q = s;
     long long delta = 0;
     for (uint32_t t = 0; t < DEC_THREADS; t++) {
+        const uint32_t lim = sub_limit(c, t, range_end_bit);
+        if (lim == 0) break;
         uint32_t end, cnt_hi;
         unsigned long long mask;
-        sub_decode_count(T, f, t * SUB_BITS, q, end, cnt_hi, mask, bad);
+        sub_decode_count(T, f, t * SUB_BITS, q, lim, end, cnt_hi, mask, bad);
         uint32_t cnt = __popcll(mask) + cnt_hi;
         uint32_t old = info[t];
         delta += (long long)cnt - (long long)(old >> 6);
-        info[t] = (uint16_t)(q | (cnt << 6));
+        info[t] = (uint16_t)((q & 63u) | (cnt << 6));
+        if (sub_limit(c, t + 1, range_end_bit) == 0) {          // the range ends in this subsequence
+            work->result[1] = end;
+            break;
+        }
         if (t + 1 == DEC_THREADS) {
             L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
             uint32_t curE = L.chunkE2[c] != 0xFFFFFFFFu ? L.chunkE2[c] : L.chunkE[c];
@@ -507,8 +530,8 @@ __device__ bool fix_chunk(const TabView &T, const uint8_t *frame, unsigned long 
 }
 
 __global__ void dec_fix_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
-                               const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                               const unsigned long long *gate)
+                               unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                               unsigned long long nch, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -518,14 +541,14 @@ __global__ void dec_fix_kernel(const uint8_t *__restrict__ frame, unsigned long 
     if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
     TabView T{tab->t1, tab->t2, tab->longs, tab->n_long};
     uint32_t bad = 0;
-    if (!fix_chunk(T, frame, frame_bytes, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
+    if (!fix_chunk(T, frame, frame_bytes, range_end_bit, work, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
 // streams that do not synchronise within a whole chunk: carry the true start forward serially
 __global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
-                                      const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                                      const unsigned long long *gate)
+                                      unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
+                                      DecWork *work, unsigned long long nch, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     if (work->flags[0] == 0 || tab->single_sym) return;
@@ -536,7 +559,7 @@ __global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigne
         if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix_kernel used
         uint32_t s = L.chunkE2[c - 1];
         if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
-        fix_chunk(T, frame, frame_bytes, L, c, s, bad);
+        fix_chunk(T, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
@@ -564,6 +587,7 @@ dec_scan_kernel(DecWork *work, unsigned long long nch, const unsigned long long 
     __syncthreads();
     unsigned long long run = x - sum + s_w[wid];
     for (unsigned long long i = lo; i < hi; i++) { L.chunkBase[i] = run; run += L.chunkCnt[i]; }
+    if (hi == nch && hi > lo) work->result[2] = run;     // symbols in the whole range
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -708,15 +732,15 @@ int launch_decode_fast(Ctx *c, const uint8_t *frame, long long hi_valid, long lo
 // the exact kernels; gate == nullptr runs them unconditionally, otherwise only when the single-pass
 // decoder raised one of DF_GATE_MASK (decided on the device: hf_decode stays asynchronous)
 static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
-                               uint64_t n_symbols, const DecodeTable *d_tab, uint16_t *out16, DecWork *work,
-                               unsigned long long nch, const unsigned long long *gate)
+                               unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
+                               uint16_t *out16, DecWork *work, unsigned long long nch, const unsigned long long *gate)
 {
-    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, gate);
+    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
     HF_LAUNCH_CHECK(c);
     if (nch > 1) {
-        HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch, gate);
+        HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
-        HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, d_tab, work, nch, gate);
+        HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
     }
     HF_PROF(c, "dec_scan_kernel"); dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch, gate);
@@ -768,7 +792,17 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
         if (rc) return rc;
         gate = reinterpret_cast<const unsigned long long *>((uint8_t *)fast_work + 16) + 3;     // DfWork::result[3]
     }
-    return launch_decode_exact(c, frame, frame_bytes, F0, n_symbols, d_tab, out16, work, nch, gate);
+    return launch_decode_exact(c, frame, frame_bytes, F0, frame_bytes * 8, n_symbols, d_tab, out16, work, nch, gate);
+}
+
+// result[4] of a range call from the exact kernels' work area: -, overflow, symbols, flags
+__global__ void dec_result_kernel(const DecWork *__restrict__ work, unsigned long long out_symbols,
+                                  unsigned long long *__restrict__ result)
+{
+    result[0] = 0;
+    result[1] = work->result[1];
+    result[2] = work->result[2];
+    result[3] = (work->flags[1] ? 4ull : 0ull) | (work->result[2] > out_symbols ? 8ull : 0ull);
 }
 
 // one rank's byte range of a sharded stream.  tail_only: just the overflow of the
@@ -781,25 +815,41 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
     if ((first_bit >> 3) > range_bytes) return set_err(c, HF_ERR_ARG, "hf_decode_range: first bit past the range");
     const uint8_t *p = d_range + (first_bit >> 3);
     const uint8_t *frame = reinterpret_cast<const uint8_t *>((uintptr_t)p & ~(uintptr_t)15);
-    const long long lead = (long long)((uintptr_t)p & 15);
-    const uint32_t F0 = (uint32_t)(lead * 8 + (first_bit & 7));
-    const long long own = (long long)(range_bytes - (first_bit >> 3));
-    const long long hi_valid = lead + own + (long long)halo_bytes;
-    const long long end_bit = (lead + own) * 8;
-    const unsigned long long nch = df_chunks((unsigned long long)end_bit);
+    const unsigned long long lead = (unsigned long long)((uintptr_t)p & 15);
+    const unsigned long long F0 = lead * 8 + (first_bit & 7);
+    const unsigned long long own = range_bytes - (first_bit >> 3);
+    const unsigned long long frame_bytes = lead + own + halo_bytes;        // readable
+    const unsigned long long end_bit = (lead + own) * 8;                   // code words starting at or after it are not ours
+    unsigned long long nch = (end_bit + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (nch == 0) nch = 1;
+    if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode_range: range too large");
     const size_t off = 8u << 20;
-    int rc = ensure_ws(c, off + df_work_bytes(nch));
+    if (!c->decode_exact_only && !tail_only) {          // the single-pass kernel (hf_set_decode_mode(ctx, 0))
+        const unsigned long long nchf = df_chunks(end_bit);
+        int rc = ensure_ws(c, off + df_work_bytes(nchf));
+        if (rc) return rc;
+        void *fast_work = (uint8_t *)c->ws + off;
+        rc = launch_decode_fast(c, frame, (long long)frame_bytes, (long long)end_bit, (uint32_t)F0, out_symbols, d_tab,
+                                reinterpret_cast<uint16_t *>(d_out), fast_work, nchf, false);
+        if (rc) return rc;
+        HF_CUDA(c, cudaMemcpyAsync(d_result, (uint8_t *)fast_work + 16, 32, cudaMemcpyDeviceToDevice, c->stream));
+        return HF_OK;
+    }
+    int rc = ensure_ws(c, off + DecLayout::bytes(nch));
     if (rc) return rc;
-    void *fast_work = (uint8_t *)c->ws + off;
-    rc = launch_decode_fast(c, frame, hi_valid, end_bit, F0, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
-                            fast_work, nch, tail_only);
-    if (rc) return rc;
-#ifdef HF_DF_TIMING
-    const size_t result_bytes = 96;                     // result[4] + phase_cycles[8]: the caller passes u64[12]
-#else
-    const size_t result_bytes = 32;
-#endif
-    HF_CUDA(c, cudaMemcpyAsync(d_result, (uint8_t *)fast_work + 16, result_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
+    HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
+    if (tail_only) {
+        // only the last chunk, from a guessed start: 16 KiB of self-synchronisation lie before the range end
+        HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
+        HF_LAUNCH_CHECK(c);
+    } else {
+        rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
+                                 work, nch, nullptr);
+        if (rc) return rc;
+    }
+    HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, tail_only ? ~0ull >> 8 : out_symbols, d_result);
+    HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 

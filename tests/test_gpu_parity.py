@@ -250,6 +250,63 @@ def test_malformed_images_are_rejected(codec, oracle, romeo):
         codec.decompress(dev(bad))
 
 
+# ---------------------------------------------------------------- sharded stream (row e), ranks emulated on one GPU
+def _decode_by_ranges(codec, image_np, cuts, exact_mode):
+    """splits the image at the byte offsets `cuts` and decodes every range on its own, as the ranks of a sharded
+    job do: range_overflow (speculative) for the hand-over bits, decode_range from the predecessor's overflow"""
+    HALO = 32
+    image = dev(np.concatenate([image_np, np.zeros(HALO + 64, np.uint8)]))
+    table, info = codec.parse_header(image[: image_np.size])
+    bounds = [0] + list(cuts) + [image_np.size]
+    codec.set_decode_mode(exact_mode)
+    try:
+        first, outs = int(info.payload_start_bit), []
+        for lo, hi in zip(bounds, bounds[1:]):
+            rb = hi - lo
+            buf = image[lo: hi + HALO].clone()                      # own allocation: aligned like a rank's slice
+            if first >= rb * 8:                                     # no code word starts in this range
+                first -= rb * 8
+                continue
+            spec = int(codec.range_overflow(buf, rb, HALO, table)[1].item())
+            out = torch.empty(int(info.original_bytes) + 64, dtype=torch.uint8, device="cuda")
+            res = codec.decode_range(buf, rb, HALO, first, table, out).tolist()
+            assert res[3] == 0, res
+            if rb >= 4096:                                          # enough bits behind the guess to synchronise
+                assert spec == res[1], (lo, hi, spec, res)
+            outs.append(out[: 2 * res[2]])
+            first = res[1]
+    finally:
+        codec.set_decode_mode(True)
+    n_even = int(info.original_bytes) & ~1
+    return torch.cat(outs)[:n_even].cpu().numpy()
+
+
+@pytest.mark.parametrize("exact_mode", [True, False])
+def test_range_decode_matches_whole_decode(codec, oracle, romeo, exact_mode):
+    rng = np.random.default_rng(21)
+    for data in (romeo, synth.zipf1g(3 << 20), CASES["uniform_64k"], CASES["two_symbols_skew"], synth.pdf15m()[: 1 << 20]):
+        image = oracle.compress(data)
+        hdr = (int(codec.parse_header(dev(image))[1].payload_start_bit) + 7) // 8
+        for world in (2, 3, 8):
+            cuts = sorted(int(x) for x in rng.integers(hdr, image.size, world - 1))
+            got = _decode_by_ranges(codec, image, cuts, exact_mode)
+            assert np.array_equal(got, data[: data.size & ~1]), (data.size, world, cuts)
+
+
+def test_sharded_codec_single_rank(codec, oracle, romeo):
+    """ShardedCodec with one rank: same stages, no collectives; byte-identical slices and round trip"""
+    from huffman_b200.sharded import ShardedCodec
+    job = ShardedCodec(codec)
+    for data in (romeo, synth.zipf1g((2 << 20) + 1), CASES["three_bytes"], CASES["single_symbol_run"]):
+        d = dev(data[: data.size & ~1]) if data.size > 1 else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        sl = job.compress(d, data.size, int(data[-1]) if data.size & 1 else 0)
+        image = job.gather_image(sl).cpu().numpy()
+        assert np.array_equal(image, oracle.compress(data))
+        back, off, n_total = job.decompress(sl)
+        assert off == 0 and n_total == data.size
+        assert np.array_equal(back.cpu().numpy(), data[: data.size & ~1])
+
+
 # ---------------------------------------------------------------- host-buffer calls and the programs (row b)
 def test_host_calls_match_device_calls(codec, oracle):
     data = synth.zipf1g((5 << 20) + 3)
