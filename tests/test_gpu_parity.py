@@ -307,6 +307,20 @@ def test_sharded_codec_single_rank(codec, oracle, romeo):
         assert np.array_equal(back.cpu().numpy(), data[: data.size & ~1])
 
 
+def test_multi_gpu_torchrun(oracle):
+    """one process per GPU over NCCL (needs >= 2 GPUs: `gpurun --gpus 2`); the same host logic runs under gloo
+    with an oracle-backed stand-in for the kernels in the CPU suite"""
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "dist_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+
+
 # ---------------------------------------------------------------- host-buffer calls and the programs (row b)
 def test_host_calls_match_device_calls(codec, oracle):
     data = synth.zipf1g((5 << 20) + 3)
