@@ -55,6 +55,7 @@ static_assert(offsetof(Codebook, p8) == offsetof(Codebook, p16) + NSYM * 2, "enc
 constexpr uint32_t K1 = 12;
 constexpr uint32_t K2MAX = 12;
 constexpr uint32_t T2_CAP = 1u << 20;          // entries; 2^K1 prefixes x 2^8 always fits
+constexpr uint32_t FLAT_MAX = 22;              // index bits of the flat second-level planes
 struct LongCode {
     unsigned long long code_left;               // left aligned in 64 bits
     uint32_t leaf;                              // (sym << 8) | len
@@ -75,6 +76,16 @@ struct DecodeTable {
     uint32_t sub_depth[1u << K1];
     uint32_t t2[T2_CAP];
     LongCode longs[NSYM];
+    // direct planes of the word-walk kernels (decode2.cu), derived from t1 / t2 by dt_planes_kernel; 0 = not here
+    //   len16   code length by the next 16 bits (<= 16)          -> shared memory of dec_sync2_kernel
+    //   lut15   (sym << 8) | len by the next 15 bits (<= 15)     -> shared memory of dec_write2_kernel
+    //   lenflat / flat2   length / (sym << 8) | len by the next k2 bits (<= k2 <= 22), L2 resident
+    uint32_t k2;
+    uint32_t pad2[3];
+    alignas(16) uint8_t len16[1u << 16];
+    alignas(16) uint32_t lut15[1u << 15];
+    alignas(16) uint8_t lenflat[1u << FLAT_MAX];
+    alignas(16) uint32_t flat2[1u << FLAT_MAX];
 };
 
 // ---- context ----------------------------------------------------------------------

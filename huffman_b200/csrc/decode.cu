@@ -29,44 +29,12 @@
 //       and writes the symbols with aligned 128-bit stores.
 //
 // Algorithmic bytes: C read + N written (the payload is read twice: traffic ~ 2C + N).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "decode_common.cuh"
 
 namespace hf {
-
-constexpr int DEC_THREADS = 512;
-constexpr uint32_t SUB_BITS = 256;                              // bits per subsequence (thread)
-constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits = 16 KiB
-constexpr uint32_t CHUNK_WORDS = CHUNK_BITS / 32;               // 4096
-constexpr uint32_t CHUNK_PAD_WORDS = 8;                         // look-ahead past the chunk
-constexpr uint32_t WIN_SYMS = 16384;                            // output staging window (symbols)
-constexpr uint32_t SW_PADDED = (smem_words_padded(CHUNK_WORDS + CHUNK_PAD_WORDS) + 3) & ~3u;   // staged chunk, padded layout
-
-// result flags of the single-pass decoder (decode_fast.cu) that send the job to the exact kernels below
-constexpr unsigned long long DF_GATE_MASK = 1 | 2 | 4 | 16;
-
-struct DecWork {
-    unsigned long long result[4];       // [1] overflow of the last code word past the range end, [2] symbols in the range
-    unsigned long long flags[4];        // [0] any chunk failed to sync, [1] invalid code met, [2] table error
-    // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32, chunkE2[nch] u32 (0xFFFFFFFF = unchanged),
-    //              info[nch * DEC_THREADS] u16
-};
-
-struct DecLayout {
-    unsigned long long *chunkBase;
-    uint32_t *chunkCnt, *chunkE, *chunkE2;
-    uint16_t *info;
-    static size_t bytes(uint64_t nch) { return sizeof(DecWork) + nch * (8 + 4 + 4 + 4 + 2 * (size_t)DEC_THREADS); }
-    __host__ __device__ DecLayout(DecWork *w, uint64_t nch)
-    {
-        uint8_t *p = reinterpret_cast<uint8_t *>(w + 1);
-        chunkBase = reinterpret_cast<unsigned long long *>(p); p += nch * 8;
-        chunkCnt = reinterpret_cast<uint32_t *>(p); p += nch * 4;
-        chunkE = reinterpret_cast<uint32_t *>(p); p += nch * 4;
-        chunkE2 = reinterpret_cast<uint32_t *>(p); p += nch * 4;
-        info = reinterpret_cast<uint16_t *>(p);
-    }
-};
 
 // -----------------------------------------------------------------------------------
 // decode-table build from (sym, len, code)[U]
@@ -371,15 +339,6 @@ __device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t
     end = pos - lim;
 }
 
-// bits of subsequence t of chunk c that lie before the end of the range (0 .. SUB_BITS)
-__device__ __forceinline__ uint32_t sub_limit(unsigned long long c, uint32_t t, unsigned long long range_end_bit)
-{
-    const unsigned long long x = c * CHUNK_BITS + (unsigned long long)t * SUB_BITS;
-    if (x >= range_end_bit) return 0u;
-    const unsigned long long room = range_end_bit - x;
-    return room >= SUB_BITS ? SUB_BITS : (uint32_t)room;
-}
-
 // Walks the code words of the subsequence at staged bit `sub0` from offset `from` up to `lim`, recording
 // every boundary in a 256-bit mask.  HIT: stop at the first position the OLD walk (mask on entry) also
 // visited and splice the old walk's remainder behind the new prefix — a re-synchronisation costs only
@@ -679,6 +638,21 @@ __global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned lo
 }
 
 // -----------------------------------------------------------------------------------
+int launch_table_planes(Ctx *c, DecodeTable *d_tab);             // decode2.cu
+int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
+                 unsigned long long c_first, unsigned long long c_last, uint32_t speculative, const unsigned long long *gate);
+int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+                  const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long n_symbols,
+                  uint16_t *out, const unsigned long long *gate);
+
+static bool use_old_kernels()
+{   // development switch: HF_DECODE_OLD=1 runs decode.cu's first-generation kernels (A/B timing)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HF_DECODE_OLD"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
 {
     // zero everything but the (large) long list; t2 zero = invalid
@@ -690,7 +664,7 @@ static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dt_fill_kernel"); dt_fill_kernel<<<NSYM / 256, 256, 0, c->stream>>>(src, d_tab);
     HF_LAUNCH_CHECK(c);
-    return HF_OK;
+    return launch_table_planes(c, d_tab);
 }
 
 int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab)
@@ -735,8 +709,14 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
                                unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
                                uint16_t *out16, DecWork *work, unsigned long long nch, const unsigned long long *gate)
 {
-    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
-    HF_LAUNCH_CHECK(c);
+    const bool old = use_old_kernels();
+    if (old) {
+        HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
+        HF_LAUNCH_CHECK(c);
+    } else {
+        int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, nch, 0u, gate);
+        if (rc) return rc;
+    }
     if (nch > 1) {
         HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
@@ -745,6 +725,7 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
     }
     HF_PROF(c, "dec_scan_kernel"); dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch, gate);
     HF_LAUNCH_CHECK(c);
+    if (!old) return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16, gate);
     const size_t wsmem = (SW_PADDED + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
     static bool wattr = false;
     if (!wattr) {
@@ -841,8 +822,13 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
     HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
     if (tail_only) {
         // only the last chunk, from a guessed start: 16 KiB of self-synchronisation lie before the range end
-        HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
-        HF_LAUNCH_CHECK(c);
+        if (use_old_kernels()) {
+            HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
+            HF_LAUNCH_CHECK(c);
+        } else {
+            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, nch, 1u, nullptr);
+            if (rc) return rc;
+        }
     } else {
         rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
                                  work, nch, nullptr);

@@ -133,6 +133,51 @@ __device__ __forceinline__ uint32_t decode_one(const TabView &T, const BitReader
     return e;
 }
 
+// ---- geometry and global work area of the exact decoder (decode.cu, decode2.cu) ----
+constexpr int DEC_THREADS = 512;
+constexpr uint32_t SUB_BITS = 256;                              // bits per subsequence (thread)
+constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits = 16 KiB
+constexpr uint32_t CHUNK_WORDS = CHUNK_BITS / 32;               // 4096
+constexpr uint32_t CHUNK_PAD_WORDS = 8;                         // look-ahead past the chunk
+constexpr uint32_t WIN_SYMS = 16384;                            // output staging window (symbols)
+constexpr uint32_t SW_PADDED = (smem_words_padded(CHUNK_WORDS + CHUNK_PAD_WORDS) + 3) & ~3u;   // staged chunk, padded layout
+
+// result flags of the single-pass decoder (decode_fast.cu) that send the job to the exact kernels below
+constexpr unsigned long long DF_GATE_MASK = 1 | 2 | 4 | 16;
+
+struct DecWork {
+    unsigned long long result[4];       // [1] overflow of the last code word past the range end, [2] symbols in the range
+    unsigned long long flags[4];        // [0] any chunk failed to sync, [1] invalid code met, [2] table error
+    // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32, chunkE2[nch] u32 (0xFFFFFFFF = unchanged),
+    //              info[nch * DEC_THREADS] u16
+};
+
+struct DecLayout {
+    unsigned long long *chunkBase;
+    uint32_t *chunkCnt, *chunkE, *chunkE2;
+    uint16_t *info;
+    static size_t bytes(uint64_t nch) { return sizeof(DecWork) + nch * (8 + 4 + 4 + 4 + 2 * (size_t)DEC_THREADS); }
+    __host__ __device__ DecLayout(DecWork *w, uint64_t nch)
+    {
+        uint8_t *p = reinterpret_cast<uint8_t *>(w + 1);
+        chunkBase = reinterpret_cast<unsigned long long *>(p); p += nch * 8;
+        chunkCnt = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        chunkE = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        chunkE2 = reinterpret_cast<uint32_t *>(p); p += nch * 4;
+        info = reinterpret_cast<uint16_t *>(p);
+    }
+};
+
+
+// bits of subsequence t of chunk c that lie before the end of the range (0 .. SUB_BITS)
+__device__ __forceinline__ uint32_t sub_limit(unsigned long long c, uint32_t t, unsigned long long range_end_bit)
+{
+    const unsigned long long x = c * CHUNK_BITS + (unsigned long long)t * SUB_BITS;
+    if (x >= range_end_bit) return 0u;
+    const unsigned long long room = range_end_bit - x;
+    return room >= SUB_BITS ? SUB_BITS : (uint32_t)room;
+}
+
 __device__ __forceinline__ uint32_t spec_start(unsigned long long X, unsigned long long F0, uint32_t g)
 {   // first offset >= 0 from frame bit X at which a code word can start (boundaries are F0 + k*g)
     if (g <= 1) return 0;
