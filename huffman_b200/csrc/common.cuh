@@ -56,6 +56,7 @@ constexpr uint32_t K1 = 12;
 constexpr uint32_t K2MAX = 12;
 constexpr uint32_t T2_CAP = 1u << 20;          // entries; 2^K1 prefixes x 2^8 always fits
 constexpr uint32_t FLAT_MAX = 22;              // index bits of the flat second-level planes
+constexpr uint32_t MICRO_K = 14;               // index bits of the shared-memory plane; micro trees add up to 4
 struct LongCode {
     unsigned long long code_left;               // left aligned in 64 bits
     uint32_t leaf;                              // (sym << 8) | len
@@ -76,14 +77,20 @@ struct DecodeTable {
     uint32_t sub_depth[1u << K1];
     uint32_t t2[T2_CAP];
     LongCode longs[NSYM];
-    // direct planes of the word-walk kernels (decode2.cu), derived from t1 / t2 by dt_planes_kernel; 0 = not here
-    //   len16   code length by the next 16 bits (<= 16)          -> shared memory of dec_sync2_kernel
-    //   lut15   (sym << 8) | len by the next 15 bits (<= 15)     -> shared memory of dec_write2_kernel
+    // planes of the word-walk kernels (decode2.cu), derived from t1 / t2 by the dt_planes / dt_micro kernels
+    //   t14     by the next 14 bits, in shared memory:
+    //             (sym << 16) | (len << 1)   a code of at most 14 bits (bit 0 clear, len >= 1)
+    //             (base << 16) | mask        every code below this prefix has 15..18 bits (a complete "micro tree" of
+    //                                        depth <= 4): mask bit j = a leaf starts at slot j of the next 4 bits
+    //                                        (bit 0 always set), its symbols are leaves[base ...] in code order
+    //             0                          deeper, incomplete or absent: take the flat planes
+    //   leaves  symbols of the micro trees, in shared memory of the write kernel
     //   lenflat / flat2   length / (sym << 8) | len by the next k2 bits (<= k2 <= 22), L2 resident
     uint32_t k2;
     uint32_t pad2[3];
-    alignas(16) uint8_t len16[1u << 16];
-    alignas(16) uint32_t lut15[1u << 15];
+    alignas(16) uint32_t t14[1u << MICRO_K];
+    alignas(16) uint16_t leaves[NSYM];
+    alignas(16) uint16_t micro_sym[16u << MICRO_K];     // build scratch: symbol at every slot of every prefix
     alignas(16) uint8_t lenflat[1u << FLAT_MAX];
     alignas(16) uint32_t flat2[1u << FLAT_MAX];
 };

@@ -641,10 +641,13 @@ __global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned lo
 int launch_table_planes(Ctx *c, DecodeTable *d_tab);             // decode2.cu
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c_first, unsigned long long c_last, uint32_t speculative, const unsigned long long *gate);
+                 bool tail_only, const unsigned long long *gate);
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long n_symbols,
                   uint16_t *out, const unsigned long long *gate);
+
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
+                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, const unsigned long long *gate);
 
 static bool use_old_kernels()
 {   // development switch: HF_DECODE_OLD=1 runs decode.cu's first-generation kernels (A/B timing)
@@ -714,10 +717,13 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
         HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
         HF_LAUNCH_CHECK(c);
     } else {
-        int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, nch, 0u, gate);
+        int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, false, gate);
         if (rc) return rc;
     }
-    if (nch > 1) {
+    if (!old) {
+        int rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
+        if (rc) return rc;
+    } else if (nch > 1) {
         HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
         HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
@@ -826,7 +832,7 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
             HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
             HF_LAUNCH_CHECK(c);
         } else {
-            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, nch, 1u, nullptr);
+            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, true, nullptr);
             if (rc) return rc;
         }
     } else {

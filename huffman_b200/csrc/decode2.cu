@@ -12,10 +12,14 @@
 //   * a thread keeps its 256-bit subsequence (+ one look-ahead word) in REGISTERS, loaded straight
 //     from global memory; the walk is unrolled over the 8 words, so the 32-bit window of a code word
 //     is ONE funnel shift of two registers — no shared-memory staging of the payload, no bit reader;
-//   * the tables are direct and much deeper: a 64 KiB length plane indexed by 16 bits (the
-//     synchronisation walks need no symbols) and a 128 KiB (symbol, length) plane indexed by 15 bits,
-//     each in the shared memory of a persistent CTA; longer codes take ONE gather from a flat
-//     second-level plane (<= 22 bits, L2 resident); anything beyond goes through decode.cu's tables;
+//   * the table of the hot loop is ONE 64 KiB shared-memory plane indexed by 14 bits whose entries are either a
+//     code word of at most 14 bits or a "micro tree": the shape (16-bit leaf-start mask) of the complete
+//     depth-4 subtree below that prefix, from which the length of a 15..18-bit code is a few bit operations and
+//     its symbol one more shared-memory load (leaves[base + rank], 128 KiB, write kernel only).  The 65,536
+//     byte pairs of a flat or mixed stream get 17/18-bit codes, so a plain direct table of that depth would
+//     need 1 MiB; here every code of up to 18 bits is resolved without leaving the SM.  Deeper or incomplete
+//     prefixes take ONE gather from a flat second-level plane (<= 22 bits, L2 resident); anything beyond goes
+//     through decode.cu's tables;
 //   * re-synchronisation is detected at four checkpoints per subsequence (the first code word boundary
 //     at or after bits 0/64/128/192, with the symbol count of every 64-bit segment), which costs two
 //     instructions per checkpoint instead of a 256-bit boundary mask maintained per symbol.
@@ -26,12 +30,12 @@
 
 namespace hf {
 
-constexpr uint32_t SYNC_K = 16;                                 // index bits of the length plane
-constexpr uint32_t WRITE_K = 15;                                // index bits of the (symbol, length) plane
-constexpr int W2_THREADS = 2 * DEC_THREADS;                     // a pair of chunks per step
-constexpr uint32_t W2_WIN = 40960;                              // output staging window (symbols)
-constexpr size_t S2_SMEM = 1u << SYNC_K;
-constexpr size_t W2_SMEM = (4u << WRITE_K) + (W2_WIN + 8) * 2;
+constexpr uint32_t MICRO_D = 4;                                 // depth of a micro tree
+constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code resolved in shared memory (18)
+constexpr int W2_THREADS = DEC_THREADS;                         // one chunk per step
+constexpr uint32_t W2_WIN = 16384;                              // output staging window (symbols)
+constexpr size_t S2_SMEM = 4u << MICRO_K;
+constexpr size_t W2_SMEM = (4u << MICRO_K) + NSYM * 2 + (W2_WIN + 8) * 2;
 
 // ---- planes ------------------------------------------------------------------------------------
 // (sym << 8) | len of the code word that is a prefix of the left-aligned window, from t1 / t2; 0 when
@@ -52,15 +56,28 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t k2 = tab->maxlen;
-    k2 = k2 < SYNC_K ? SYNC_K : (k2 > FLAT_MAX ? FLAT_MAX : k2);
+    k2 = k2 < MICRO_K ? MICRO_K : (k2 > FLAT_MAX ? FLAT_MAX : k2);
     if (i == 0) tab->k2 = k2;
-    if (i < (1u << SYNC_K)) {
-        const uint32_t e = lookup_win32(tab, i << (32 - SYNC_K));
-        tab->len16[i] = (e & 0x7Fu) <= SYNC_K ? (uint8_t)(e & 0x7Fu) : (uint8_t)0;
-    }
-    if (i < (1u << WRITE_K)) {
-        const uint32_t e = lookup_win32(tab, i << (32 - WRITE_K));
-        tab->lut15[i] = (e & 0x7Fu) <= WRITE_K ? e : 0u;
+    if (i < (1u << MICRO_K)) {
+        // entry of the 14-bit prefix i: a short code, or the shape of the micro tree below it
+        const uint32_t w0 = i << (32 - MICRO_K);
+        const uint32_t e0 = lookup_win32(tab, w0);
+        uint32_t entry = 0;
+        if (e0 && (e0 & 0x7Fu) <= MICRO_K) {
+            entry = ((e0 >> 8) << 16) | ((e0 & 0x7Fu) << 1);
+        } else {
+            uint32_t mask = 0;
+            bool ok = true;
+            for (uint32_t j = 0; j < (1u << MICRO_D); j++) {
+                const uint32_t e = lookup_win32(tab, w0 | (j << (32 - MICRO_MAX)));
+                const uint32_t len = e & 0x7Fu;
+                if (e == 0 || len <= MICRO_K || len > MICRO_MAX) { ok = false; break; }
+                tab->micro_sym[i * (1u << MICRO_D) + j] = (uint16_t)(e >> 8);
+                if ((j & ((1u << (MICRO_MAX - len)) - 1u)) == 0) mask |= 1u << j;       // first slot of its leaf
+            }
+            if (ok) entry = mask;                       // the base comes from dt_micro_kernel
+        }
+        tab->t14[i] = entry;
     }
     if (i < (1u << k2)) {
         const uint32_t e = lookup_win32(tab, i << (32 - k2));
@@ -70,11 +87,66 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
     }
 }
 
+// bases of the micro trees (exclusive scan of their leaf counts in prefix order) and the leaf symbols
+__global__ void __launch_bounds__(1024, 1)
+dt_micro_kernel(DecodeTable *__restrict__ tab)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr uint32_t PER = (1u << MICRO_K) / 1024;    // 16 prefixes per thread
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < PER; j++) {
+        const uint32_t e = tab->t14[tid * PER + j];
+        if (e & 1u) sum += __popc(e & 0xFFFFu);
+    }
+    uint32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = s_w[lane];
+        uint32_t t = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        s_w[lane] = t - v;
+    }
+    __syncthreads();
+    uint32_t base = x - sum + s_w[wid];
+    for (uint32_t j = 0; j < PER; j++) {
+        const uint32_t p = tid * PER + j;
+        const uint32_t e = tab->t14[p];
+        if (!(e & 1u)) continue;
+        const uint32_t mask = e & 0xFFFFu;
+        if (base + __popc(mask) > NSYM) { tab->t14[p] = 0; continue; }     // cannot happen for a prefix code
+        tab->t14[p] = (base << 16) | mask;
+        for (uint32_t m = mask; m; m &= m - 1)
+            tab->leaves[base++] = tab->micro_sym[p * (1u << MICRO_D) + (__ffs(m) - 1)];
+    }
+}
+
 int launch_table_planes(Ctx *c, DecodeTable *d_tab)
 {
     HF_PROF(c, "dt_planes_kernel"); dt_planes_kernel<<<(1u << FLAT_MAX) / 256, 256, 0, c->stream>>>(d_tab);
     HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dt_micro_kernel"); dt_micro_kernel<<<1, 1024, 0, c->stream>>>(d_tab);
+    HF_LAUNCH_CHECK(c);
     return HF_OK;
+}
+
+// length of the code word at the head of `win` from a micro-tree entry e (bit 0 set)
+__device__ __forceinline__ uint32_t micro_len(uint32_t e, uint32_t b)
+{
+    const uint32_t mask = e & 0xFFFFu;
+    const uint32_t y = mask << (31 - b);                // leaf starts at or below slot b, slot b in bit 31
+    const uint32_t x = (mask | 0x10000u) >> (b + 1);    // leaf starts above slot b, sentinel at slot 16
+    const uint32_t size = __clz(y) + __ffs(x);          // slots of the leaf that holds b: 1, 2, 4, 8 or 16
+    return __clz(size) - (31 - MICRO_MAX);              // MICRO_MAX - log2(size)
+}
+__device__ __forceinline__ uint32_t micro_slot(uint32_t win) { return (win >> (32 - MICRO_MAX)) & ((1u << MICRO_D) - 1u); }
+__device__ __forceinline__ uint32_t micro_leaf(uint32_t e, uint32_t b)
+{
+    return (e >> 16) + __popc(e & 0xFFFFu & ((2u << b) - 1u)) - 1u;
 }
 
 // ---- the rare way: any code length, bits straight from global memory ----------------------------
@@ -105,7 +177,7 @@ __device__ __noinline__ uint32_t slow_decode(const DecodeTable *tab, const uint8
     return e;
 }
 
-// ---- a thread's subsequence in registers --------------------------------------------------------
+// ---- a thread's subsequence in registers (write kernel) ------------------------------------------
 // r[0..7]: the 8 big-endian words of subsequence (c, t); r[8]: the first word of the next one
 __device__ __forceinline__ void load_sub(uint32_t (&r)[9], const uint8_t *frame, unsigned long long frame_bytes,
                                          unsigned long long c, uint32_t t, uint32_t lane)
@@ -124,128 +196,209 @@ __device__ __forceinline__ void load_sub(uint32_t (&r)[9], const uint8_t *frame,
     r[8] = nx;
 }
 
-// Walks the code words of a subsequence from bit `start` to `lim`.  chkpos: byte k = (first code word
-// boundary at or after bit 64k) - 64k; chkcnt: byte k = code words starting in [64k, 64k + 64).
-// RESYNC: chkpos / chkcnt describe an earlier walk; stop at the first checkpoint both walks share and
-// keep the earlier walk's record from there on (`end` is then the earlier walk's).  CHK_NONE marks "no
-// earlier walk": its bytes (0xFF) equal no checkpoint offset (those are below 192).
+// ---- synchronisation kernel ---------------------------------------------------------------------
+// A thread walks a SPAN of 4 subsequences (1024 bits).  Longer spans mean fewer repeated walks: a walk
+// from a wrong start re-joins the true one after tens of bits on skewed codes but only after ~2,000 bits
+// on the nearly fixed-length codes of flat data, and every subsequence a wrong walk crosses costs the
+// fix-point one more round.  A CTA of 1024 threads stages a GROUP of 8 chunks (128 KiB) in shared memory,
+// one padded row of 33 words per thread (bank = (thread + word) mod 32; the pad word repeats the next
+// row's first word so a 32-bit window never leaves the row).
+constexpr int S3_THREADS = 1024;
+constexpr uint32_t SPAN_SUBS = 4;
+constexpr uint32_t SPAN_BITS = SPAN_SUBS * SUB_BITS;            // 1024
+constexpr uint32_t SPAN_WORDS = SPAN_BITS / 32;                 // 32
+constexpr uint32_t ROW_WORDS = SPAN_WORDS + 1;
+constexpr uint32_t GROUP_CHUNKS = S3_THREADS * SPAN_SUBS / DEC_THREADS;    // 8
+constexpr unsigned long long GROUP_BITS = (unsigned long long)S3_THREADS * SPAN_BITS;
+constexpr uint32_t SEG_BITS = 128;                              // checkpoint spacing
+constexpr uint32_t NSEG = SPAN_BITS / SEG_BITS;                 // 8
+constexpr size_t S3_SMEM = (4u << MICRO_K) + (size_t)S3_THREADS * ROW_WORDS * 4;
+
+// Record of a walk: chkpos byte k = (first code word boundary at or after bit 128k) - 128k; chkcnt byte k = code
+// words starting in [128k, 128k + 128).  CHK_NONE (bytes 0xFF, no checkpoint offset is that large) = no walk yet.
+struct Chk { uint32_t pos[2], cnt[2]; };
 constexpr uint32_t CHK_NONE = 0xFFFFFFFFu;
+
+// Walks the code words of a span from bit `start` to `lim`.  RESYNC: `rec` describes an earlier walk; stop at
+// the first checkpoint both walks share and keep the earlier record from there on (`end` stays the earlier one's).
 template <bool RESYNC>
-__device__ __forceinline__ void walk_len(const uint32_t (&r)[9], const uint8_t *s_len, const DecodeTable *tab,
-                                         const uint8_t *frame, unsigned long long frame_bytes, unsigned long long sub_bit0,
-                                         uint32_t k2shift, uint32_t start, uint32_t lim, uint32_t &chkpos,
-                                         uint32_t &chkcnt, uint32_t &end, uint32_t &bad)
+__device__ __forceinline__ void walk_span(const uint32_t *row, const uint32_t *s_t14, const DecodeTable *tab,
+                                          const uint8_t *frame, unsigned long long frame_bytes,
+                                          unsigned long long span_bit0, uint32_t k2shift, uint32_t start, uint32_t lim,
+                                          Chk &rec, uint32_t &end, uint32_t &bad)
 {
-    uint32_t pos = start, n = 0, npos = 0, ncnt = 0, wl = lim, keep = 0;
+    uint32_t pos = start, n = 0, wl = lim;
+    uint32_t npos[2] = {0, 0}, ncnt[2] = {0, 0};
+    int kept = NSEG;                                    // checkpoints >= kept keep the earlier record
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        if ((w & 1) == 0) {
-            const int k = w >> 1;
-            if (k > 0) { ncnt |= n << (8 * (k - 1)); n = 0; }
-            const uint32_t rel = (pos - 32u * w) & 0xFFu;
-            if (RESYNC && k > 0) {       // still walking, and on the earlier walk's boundary: the walks have met
-                if (pos < wl && rel == ((chkpos >> (8 * k)) & 0xFFu)) { wl = 0; keep = 0xFFFFFFFFu << (8 * k); }
-            }
-            npos |= rel << (8 * k);
+    for (int k = 0; k < (int)NSEG; k++) {
+        if (k > 0) { ncnt[(k - 1) >> 2] |= n << (8 * ((k - 1) & 3)); n = 0; }
+        const uint32_t rel = (pos - SEG_BITS * k) & 0xFFu;
+        if (RESYNC && k > 0) {          // still walking, and on the earlier walk's boundary: the walks have met
+            if (pos < wl && rel == ((rec.pos[k >> 2] >> (8 * (k & 3))) & 0xFFu)) { wl = 0; kept = k; }
         }
-        const uint32_t lw = min(wl, 32u * (w + 1));
+        npos[k >> 2] |= rel << (8 * (k & 3));
+        const uint32_t lw = min(wl, SEG_BITS * (k + 1));
         while (pos < lw) {
-            const uint32_t win = __funnelshift_l(r[w + 1], r[w], pos);
-            uint32_t len = s_len[win >> (32 - SYNC_K)];
-            if (len == 0) {
-                len = __ldg(tab->lenflat + (win >> k2shift));
+            const uint32_t *wp = row + (pos >> 5);
+            const uint32_t win = __funnelshift_l(wp[1], wp[0], pos);
+            const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
+            uint32_t len;
+            if (e14 & 1u) {
+                len = micro_len(e14, micro_slot(win));
+            } else {
+                len = (e14 >> 1) & 0x7Fu;
                 if (len == 0) {
-                    const uint32_t e = slow_decode(tab, frame, frame_bytes, sub_bit0 + pos);
-                    bad |= e >> 31;
-                    len = e & 0x7Fu;
+                    len = __ldg(tab->lenflat + (win >> k2shift));
+                    if (len == 0) {
+                        const uint32_t e = slow_decode(tab, frame, frame_bytes, span_bit0 + pos);
+                        bad |= e >> 31;
+                        len = e & 0x7Fu;
+                    }
                 }
             }
             pos += len;
             n++;
         }
     }
-    ncnt |= n << 24;
-    if (RESYNC && keep) {
-        chkpos = (npos & ~keep) | (chkpos & keep);
-        chkcnt = (ncnt & ~keep) | (chkcnt & keep);
+    ncnt[1] |= n << 24;
+    if (RESYNC && kept < (int)NSEG) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            // bytes of half h that belong to checkpoints >= kept
+            const int first = kept - 4 * h;             // first kept byte of this half (may be <= 0 or >= 4)
+            const uint32_t keep = first <= 0 ? 0xFFFFFFFFu : (first >= 4 ? 0u : 0xFFFFFFFFu << (8 * first));
+            rec.pos[h] = (npos[h] & ~keep) | (rec.pos[h] & keep);
+            rec.cnt[h] = (ncnt[h] & ~keep) | (rec.cnt[h] & keep);
+        }
     } else {
-        chkpos = npos;
-        chkcnt = ncnt;
+        rec.pos[0] = npos[0]; rec.pos[1] = npos[1];
+        rec.cnt[0] = ncnt[0]; rec.cnt[1] = ncnt[1];
         end = pos - lim;
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DEC_THREADS, 3)
-dec_sync2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+__device__ __forceinline__ uint32_t span_limit(unsigned long long X, unsigned long long range_end_bit)
+{   // bits of the span at frame bit X that lie before the end of the range (0 .. SPAN_BITS)
+    if (X >= range_end_bit) return 0u;
+    const unsigned long long room = range_end_bit - X;
+    return room >= SPAN_BITS ? SPAN_BITS : (uint32_t)room;
+}
+
+__global__ void __launch_bounds__(S3_THREADS, 1)
+dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                 unsigned long long nch, unsigned long long c_first, unsigned long long c_last, uint32_t speculative,
+                 unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative,
                  const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;        // the single-pass decoder succeeded
-    extern __shared__ __align__(16) uint8_t s_len[];    // 2^SYNC_K
-    __shared__ uint32_t s_end[DEC_THREADS];
-    __shared__ uint32_t s_red[DEC_THREADS / 32];
+    extern __shared__ __align__(16) uint32_t s3_smem[];
+    uint32_t *s_t14 = s3_smem;                          // 2^MICRO_K
+    uint32_t *s_bits = s3_smem + (1u << MICRO_K);       // S3_THREADS rows of ROW_WORDS
+    __shared__ uint32_t s_wend[S3_THREADS / 32];
+    __shared__ uint32_t s_red[S3_THREADS / 32];
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
     DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->len16);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_len);
-        for (uint32_t i = tid; i < S2_SMEM / 16; i += DEC_THREADS) dst[i] = __ldg(src + i);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
+        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
     }
     const uint32_t g = speculative ? 1u : tab->len_gcd;
     const uint32_t k2shift = 32u - tab->k2;
-    const uint32_t sub0 = tid * SUB_BITS;
+    const uint32_t *row = s_bits + tid * ROW_WORDS;
     uint32_t bad = 0;
 
-    for (unsigned long long c = c_first + blockIdx.x; c < c_last; c += gridDim.x) {
-        __syncthreads();                                // planes loaded / s_end, s_red reuse
-        uint32_t r[9];
-        load_sub(r, frame, frame_bytes, c, tid, lane);
-        const unsigned long long X = c * CHUNK_BITS + sub0;
-        const uint32_t lim = sub_limit(c, tid, range_end_bit);      // code words starting at or after the range end are not ours
-        const bool fixed = (c == 0 && tid == 0 && !speculative);    // holds the first payload bit: exact start
+    for (unsigned long long grp = g_first + blockIdx.x; grp < g_last; grp += gridDim.x) {
+        __syncthreads();                                // planes loaded / s_bits, s_wend, s_red reuse
+        // ---- stage the group's 128 KiB: 8 coalesced 128-bit loads per thread ----
+        const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
+#pragma unroll
+        for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
+            const uint32_t v = tid + k * S3_THREADS;    // 16-byte vector of the group
+            const unsigned long long b = gbyte0 + 16ull * v;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (b < frame_bytes) x = ld_stream_v4(frame + b);          // the frame is 16-byte aligned
+            uint32_t *dst = s_bits + (v >> 3) * ROW_WORDS + 4 * (v & 7);
+            dst[0] = bswap32(x.x); dst[1] = bswap32(x.y); dst[2] = bswap32(x.z); dst[3] = bswap32(x.w);
+        }
+        {   // the pad word of my row: the first word of the next span
+            const unsigned long long b = gbyte0 + (unsigned long long)(tid + 1) * (SPAN_BITS / 8);
+            uint32_t x = 0;
+            if (b < frame_bytes) x = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b)));
+            s_bits[tid * ROW_WORDS + SPAN_WORDS] = x;
+        }
+        __syncthreads();
+
+        const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tid * SPAN_BITS;
+        const uint32_t lim = span_limit(X, range_end_bit);     // code words starting at or after the range end are not ours
+        const bool fixed = (grp == 0 && tid == 0 && !speculative);  // holds the first payload bit: exact start
         uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
-        uint32_t end = 0, chkpos = CHK_NONE, chkcnt = 0;
+        uint32_t end = 0;
+        Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
         if (lim) {
-            if (p < lim) walk_len<false>(r, s_len, tab, frame, frame_bytes, X, k2shift, p, lim, chkpos, chkcnt, end, bad);
+            if (p < lim) walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
             else end = p - lim;
         }
-        // fix-point: my true start is my predecessor's overflow
-        for (uint32_t it = 0; it < DEC_THREADS + 1; it++) {
-            s_end[tid] = end;
-            __syncthreads();
-            int changed = 0;
-            if (tid > 0 && !fixed && lim) {
-                const uint32_t q = s_end[tid - 1];
-                if (q != p) {
-                    const uint32_t old_end = end;
-                    if (q < lim) walk_len<true>(r, s_len, tab, frame, frame_bytes, X, k2shift, q, lim, chkpos, chkcnt, end, bad);
-                    else { chkpos = CHK_NONE; chkcnt = 0; end = q - lim; }
-                    changed = end != old_end;
+        // Fix-point: my true start is my predecessor's overflow.  Inside a warp the overflows travel by
+        // shuffle and the warps iterate on their own; the warps then exchange their last overflow through
+        // shared memory, which usually moves only lane 0 of each warp.
+        const bool movable = !fixed && lim != 0;
+        uint32_t q0 = p;                                // lane 0's start: the guess, then the previous warp's overflow
+        for (uint32_t round = 0; round < S3_THREADS / 32 + 2; round++) {
+            for (;;) {
+                uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
+                if (lane == 0) q = q0;
+                const bool need = movable && q != p;
+                if (!__any_sync(0xFFFFFFFFu, need)) break;
+                if (need) {
+                    if (q < lim) walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                    else { rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim; }
                     p = q;
                 }
             }
-            if (!__syncthreads_or(changed)) break;
+            if (lane == 31) s_wend[wid] = end;
+            __syncthreads();
+            q0 = wid ? s_wend[wid - 1] : p;
+            if (!__syncthreads_or(lane == 0 && movable && q0 != p)) break;
         }
-        const uint32_t cnt = __dp4a(chkcnt, 0x01010101u, 0u);
-        L.info[c * DEC_THREADS + tid] = (uint16_t)((p & 63u) | (cnt << 6));
-        uint32_t v = cnt;
+
+        // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
+        uint32_t cnt4[SPAN_SUBS];
+        uint32_t total = 0;
+        unsigned long long packed = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < SPAN_SUBS; j++) {
+            const uint32_t pj = (rec.pos[j >> 1] >> (16 * (j & 1))) & 0xFFu;            // checkpoint 2j
+            const uint32_t cj = (rec.cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;          // segments 2j, 2j + 1
+            cnt4[j] = (cj & 0xFFu) + (cj >> 8);
+            total += cnt4[j];
+            packed |= (unsigned long long)((pj & 63u) | (cnt4[j] << 6)) << (16 * j);
+        }
+        const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tid * SPAN_SUBS;
+        if (sub_index < nch * DEC_THREADS)              // info holds whole chunks: 4 records never straddle its end
+            *reinterpret_cast<unsigned long long *>(L.info + sub_index) = packed;
+        // chunk totals: a chunk is 128 consecutive threads (4 warps)
+        uint32_t v = total;
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) s_red[tid >> 5] = v;
+        if (lane == 0) s_red[wid] = v;
         __syncthreads();
-        if (tid == 0) {
-            uint32_t tot = 0;
+        constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
+        const unsigned long long c = grp * GROUP_CHUNKS + tid / TPC;
+        if (c < nch) {
+            if (tid % TPC == 0) {
+                uint32_t tot = 0;
 #pragma unroll
-            for (int i = 0; i < DEC_THREADS / 32; i++) tot += s_red[i];
-            L.chunkCnt[c] = tot;
-            L.chunkE2[c] = 0xFFFFFFFFu;
+                for (uint32_t i = 0; i < TPC / 32; i++) tot += s_red[wid + i];
+                L.chunkCnt[c] = tot;
+                L.chunkE2[c] = 0xFFFFFFFFu;
+            }
+            if (tid % TPC == TPC - 1) L.chunkE[c] = end;
         }
-        if (tid == DEC_THREADS - 1) L.chunkE[c] = end;
-        // the thread whose subsequence holds the end of the range reports the overflow past it
-        if (lim && sub_limit(c, tid + 1, range_end_bit) == 0) work->result[1] = end;
+        // the thread whose span holds the end of the range reports the overflow past it
+        if (lim && span_limit(X + SPAN_BITS, range_end_bit) == 0) work->result[1] = end;
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
@@ -258,55 +411,55 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     extern __shared__ __align__(16) uint32_t w2_smem[];
-    uint32_t *s_lut = w2_smem;                                              // 2^WRITE_K
-    uint16_t *sout = reinterpret_cast<uint16_t *>(s_lut + (1u << WRITE_K)); // W2_WIN + 8
+    uint32_t *s_t14 = w2_smem;                                                  // 2^MICRO_K
+    uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
+    uint16_t *sout = s_leaves + NSYM;                                           // W2_WIN + 8
     __shared__ uint32_t s_w[33];
     if (tab->single_sym) return;
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->lut15);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t i = tid; i < (4u << WRITE_K) / 16; i += W2_THREADS) dst[i] = __ldg(src + i);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
+        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W2_THREADS) dst[i] = __ldg(src + i);
+        src = reinterpret_cast<const uint4 *>(tab->leaves);
+        dst = reinterpret_cast<uint4 *>(s_leaves);
+        for (uint32_t i = tid; i < NSYM * 2 / 16; i += W2_THREADS) dst[i] = __ldg(src + i);
     }
     const uint32_t k2shift = 32u - tab->k2;
-    const uint32_t half = tid / DEC_THREADS, t = tid % DEC_THREADS;
-    const uint32_t sub0 = t * SUB_BITS;
+    const uint32_t sub0 = tid * SUB_BITS;
     uint32_t bad = 0;
-    const unsigned long long npair = (nch + 1) / 2;
 
-    for (unsigned long long cp = blockIdx.x; cp < npair; cp += gridDim.x) {
+    for (unsigned long long c = blockIdx.x; c < nch; c += gridDim.x) {
         __syncthreads();                                // planes loaded / sout, s_w reuse
-        const unsigned long long c = 2 * cp + half;
-        const bool have = c < nch;
-        const unsigned long long base = L.chunkBase[2 * cp];
+        const unsigned long long base = L.chunkBase[c];
         if (base >= n_symbols) continue;                // uniform over the CTA
-        const uint32_t inf = have ? L.info[c * DEC_THREADS + t] : 0u;
+        const uint32_t inf = L.info[c * DEC_THREADS + tid];
         const uint32_t cnt = inf >> 6;
-        uint32_t pos = (c == 0 && t == 0) ? (uint32_t)F0 : (inf & 63u);     // the stream head may sit past bit 63
+        uint32_t pos = (c == 0 && tid == 0) ? (uint32_t)F0 : (inf & 63u);   // the stream head may sit past bit 63
         uint32_t r[9];
-        load_sub(r, frame, frame_bytes, have ? c : 0ull, t, lane);
+        load_sub(r, frame, frame_bytes, c, tid, lane);
 
-        // exclusive scan of the counts over the pair
+        // exclusive scan of the counts over the chunk
         uint32_t x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
         if (lane == 31) s_w[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            const uint32_t s = s_w[lane];
-            uint32_t v = s;
+            const uint32_t sv = lane < W2_THREADS / 32 ? s_w[lane] : 0u;
+            uint32_t v = sv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += y; }
-            s_w[lane] = v - s;
+            if (lane < W2_THREADS / 32) s_w[lane] = v - sv;
             if (lane == 31) s_w[32] = v;
         }
         __syncthreads();
-        const uint32_t off = x - cnt + s_w[wid];        // pair-relative index of my first symbol
+        const uint32_t off = x - cnt + s_w[wid];        // chunk-relative index of my first symbol
         unsigned long long total = s_w[32];
         if (base + total > n_symbols) total = n_symbols - base;   // garbage past the payload end is dropped
         const uint32_t my_end = (uint32_t)min((unsigned long long)(off + cnt), total);
-        uint32_t o = off;                               // pair-relative index of my next symbol
+        uint32_t o = off;                               // chunk-relative index of my next symbol
 
         const uint32_t mis = (uint32_t)(base & 7);      // staging slot j <-> output symbol base - mis + j
         for (unsigned long long w0 = 0; w0 < total; w0 += W2_WIN) {
@@ -320,16 +473,27 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                     const uint32_t lw = 32u * (w + 1);
                     while (pos < lw && sp < sp_end) {
                         const uint32_t win = __funnelshift_l(r[w + 1], r[w], pos);
-                        uint32_t e = s_lut[win >> (32 - WRITE_K)];
-                        if (e == 0) {
-                            e = __ldg(tab->flat2 + (win >> k2shift));
-                            if (e == 0) {
-                                e = slow_decode(tab, frame, frame_bytes, c * CHUNK_BITS + sub0 + pos);
-                                bad |= e >> 31;
+                        const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
+                        uint32_t len, sym;
+                        if (e14 & 1u) {
+                            const uint32_t b = micro_slot(win);
+                            len = micro_len(e14, b);
+                            sym = s_leaves[micro_leaf(e14, b)];
+                        } else {
+                            len = (e14 >> 1) & 0x7Fu;
+                            sym = e14 >> 16;
+                            if (len == 0) {
+                                uint32_t e = __ldg(tab->flat2 + (win >> k2shift));
+                                if (e == 0) {
+                                    e = slow_decode(tab, frame, frame_bytes, c * CHUNK_BITS + sub0 + pos);
+                                    bad |= e >> 31;
+                                }
+                                len = e & 0x7Fu;
+                                sym = (e >> 8) & 0xFFFFu;
                             }
                         }
-                        *sp++ = (uint16_t)(e >> 8);
-                        pos += e & 0x7Fu;
+                        *sp++ = (uint16_t)sym;
+                        pos += len;
                     }
                 }
                 o = o_end;
@@ -355,21 +519,158 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
 }
 
 // -------------------------------------------------------------------------------------------------
+// Inter-group repair.  A group converges on a GUESSED start of its first span; its true start is the overflow
+// of the group before.  One thread per chunk boundary walks from the true start, subsequence by subsequence
+// (registers + the t14 plane read through L1), until it lands on a start the synchronisation kernel recorded.
+__device__ __forceinline__ void load_sub_single(uint32_t (&r)[9], const uint8_t *frame, unsigned long long frame_bytes,
+                                                unsigned long long c, uint32_t t)
+{
+    const unsigned long long b = c * (CHUNK_BITS / 8) + (unsigned long long)t * (SUB_BITS / 8);
+    uint4 a = make_uint4(0, 0, 0, 0), d = make_uint4(0, 0, 0, 0);
+    if (b < frame_bytes) a = __ldg(reinterpret_cast<const uint4 *>(frame + b));
+    if (b + 16 < frame_bytes) d = __ldg(reinterpret_cast<const uint4 *>(frame + b + 16));
+    r[0] = bswap32(a.x); r[1] = bswap32(a.y); r[2] = bswap32(a.z); r[3] = bswap32(a.w);
+    r[4] = bswap32(d.x); r[5] = bswap32(d.y); r[6] = bswap32(d.z); r[7] = bswap32(d.w);
+    r[8] = 0;
+    if (b + 32 < frame_bytes) r[8] = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b + 32)));
+}
+
+// code words of subsequence (c, t) starting in [q, lim): their number and the overflow of the last one
+__device__ __forceinline__ void sub_count(const DecodeTable *tab, const uint8_t *frame, unsigned long long frame_bytes,
+                                          unsigned long long c, uint32_t t, uint32_t q, uint32_t lim, uint32_t k2shift,
+                                          uint32_t &end, uint32_t &cnt, uint32_t &bad)
+{
+    cnt = 0;
+    if (q >= lim) { end = q - lim; return; }
+    uint32_t r[9];
+    load_sub_single(r, frame, frame_bytes, c, t);
+    uint32_t pos = q, n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t lw = min(lim, 32u * (w + 1));
+        while (pos < lw) {
+            const uint32_t win = __funnelshift_l(r[w + 1], r[w], pos);
+            const uint32_t e14 = __ldg(tab->t14 + (win >> (32 - MICRO_K)));
+            uint32_t len;
+            if (e14 & 1u) {
+                len = micro_len(e14, micro_slot(win));
+            } else {
+                len = (e14 >> 1) & 0x7Fu;
+                if (len == 0) {
+                    len = __ldg(tab->lenflat + (win >> k2shift));
+                    if (len == 0) {
+                        const uint32_t e = slow_decode(tab, frame, frame_bytes, c * CHUNK_BITS + t * SUB_BITS + pos);
+                        bad |= e >> 31;
+                        len = e & 0x7Fu;
+                    }
+                }
+            }
+            pos += len;
+            n++;
+        }
+    }
+    cnt = n;
+    end = pos - lim;
+}
+
+// repairs chunk c from the true start `s` (offset inside the chunk's subsequence 0).
+// Returns true when the walk re-joined the recorded chain before the chunk ended.
+__device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigned long long frame_bytes,
+                           unsigned long long range_end_bit, DecWork *work, DecLayout &L, unsigned long long c, uint32_t s,
+                           uint32_t &bad)
+{
+    uint16_t *info = L.info + c * DEC_THREADS;
+    const uint32_t k2shift = 32u - tab->k2;
+    uint32_t q = s;
+    long long delta = 0;
+    for (uint32_t t = 0; t < DEC_THREADS; t++) {
+        const uint32_t lim = sub_limit(c, t, range_end_bit);
+        if (lim == 0) break;
+        uint32_t end, cnt;
+        sub_count(tab, frame, frame_bytes, c, t, q, lim, k2shift, end, cnt, bad);
+        const uint32_t old = info[t];
+        delta += (long long)cnt - (long long)(old >> 6);
+        info[t] = (uint16_t)((q & 63u) | (cnt << 6));
+        if (sub_limit(c, t + 1, range_end_bit) == 0) {          // the range ends in this subsequence
+            work->result[1] = end;
+            break;
+        }
+        if (t + 1 == DEC_THREADS) {
+            L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
+            const uint32_t curE = L.chunkE2[c] != 0xFFFFFFFFu ? L.chunkE2[c] : L.chunkE[c];
+            if (end != curE) { L.chunkE2[c] = end; return false; }
+            return true;
+        }
+        if ((uint32_t)(info[t + 1] & 63u) == end) break;
+        q = end;
+    }
+    L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
+    return true;
+}
+
+__global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
+                                unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                                unsigned long long nch, const unsigned long long *gate)
+{
+    if (gate && !(*gate & DF_GATE_MASK)) return;
+    const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (c >= nch || tab->single_sym) return;
+    DecLayout L(work, nch);
+    const uint32_t s = L.chunkE[c - 1];
+    if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
+    uint32_t bad = 0;
+    if (!fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// streams that do not synchronise within a whole chunk: carry the true start forward serially
+__global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
+                                       unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
+                                       DecWork *work, unsigned long long nch, const unsigned long long *gate)
+{
+    if (gate && !(*gate & DF_GATE_MASK)) return;
+    if (work->flags[0] == 0 || tab->single_sym) return;
+    DecLayout L(work, nch);
+    uint32_t bad = 0;
+    for (unsigned long long c = 1; c < nch; c++) {
+        if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix2_kernel used
+        const uint32_t s = L.chunkE2[c - 1];
+        if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
+        fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
+                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, const unsigned long long *gate)
+{
+    if (nch <= 1) return HF_OK;
+    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c_first, unsigned long long c_last, uint32_t speculative, const unsigned long long *gate)
+                 bool tail_only, const unsigned long long *gate)
 {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_sync2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         attr = true;
     }
-    unsigned long long grid = c_last - c_first;
-    if (grid > (unsigned long long)(3 * c->sm_count)) grid = 3 * c->sm_count;
-    HF_PROF(c, "dec_sync2_kernel");
-    dec_sync2_kernel<<<(unsigned)grid, DEC_THREADS, S2_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
-                                                                        c_first, c_last, speculative, gate);
+    const unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
+    // tail_only: the overflow past the range end, speculatively from a guessed start one or two groups
+    // (128 .. 256 KiB of self-synchronisation) before it
+    const unsigned long long g_first = tail_only ? (ngroups > 2 ? ngroups - 2 : 0) : 0;
+    unsigned long long grid = ngroups - g_first;
+    if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
+    HF_PROF(c, "dec_sync3_kernel");
+    dec_sync3_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
+                                                                       g_first, ngroups, tail_only ? 1u : 0u, gate);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -383,7 +684,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
         HF_CUDA(c, cudaFuncSetAttribute(dec_write2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
         attr = true;
     }
-    unsigned long long grid = (nch + 1) / 2;
+    unsigned long long grid = nch;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write2_kernel");
     dec_write2_kernel<<<(unsigned)grid, W2_THREADS, W2_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out, gate);

@@ -156,7 +156,7 @@ struct DecLayout {
     unsigned long long *chunkBase;
     uint32_t *chunkCnt, *chunkE, *chunkE2;
     uint16_t *info;
-    static size_t bytes(uint64_t nch) { return sizeof(DecWork) + nch * (8 + 4 + 4 + 4 + 2 * (size_t)DEC_THREADS); }
+    static size_t bytes(uint64_t nch) { return sizeof(DecWork) + nch * (8 + 4 + 4 + 4 + 2 * (size_t)DEC_THREADS) + 16; }
     __host__ __device__ DecLayout(DecWork *w, uint64_t nch)
     {
         uint8_t *p = reinterpret_cast<uint8_t *>(w + 1);
@@ -164,7 +164,7 @@ struct DecLayout {
         chunkCnt = reinterpret_cast<uint32_t *>(p); p += nch * 4;
         chunkE = reinterpret_cast<uint32_t *>(p); p += nch * 4;
         chunkE2 = reinterpret_cast<uint32_t *>(p); p += nch * 4;
-        info = reinterpret_cast<uint16_t *>(p);
+        info = reinterpret_cast<uint16_t *>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);   // 64-bit stores of 4 records
     }
 };
 
