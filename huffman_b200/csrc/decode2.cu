@@ -32,10 +32,13 @@ namespace hf {
 
 constexpr uint32_t MICRO_D = 4;                                 // depth of a micro tree
 constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code resolved in shared memory (18)
-constexpr int W2_THREADS = DEC_THREADS;                         // one chunk per step
-constexpr uint32_t W2_WIN = 16384;                              // output staging window (symbols)
-constexpr size_t S2_SMEM = 4u << MICRO_K;
-constexpr size_t W2_SMEM = (4u << MICRO_K) + NSYM * 2 + (W2_WIN + 8) * 2;
+#ifndef W3_WARPS
+#define W3_WARPS 24                                             // warps of the write kernel's CTA
+#endif
+constexpr int W3_THREADS = W3_WARPS * 32;
+// output staging window of one warp (symbols, multiple of 8): what is left of the SM's 227 KiB beside the planes
+constexpr uint32_t W3_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - 64u) / W3_WARPS) / 2 - 8) & ~7u;
+constexpr size_t W3_SMEM = (4u << MICRO_K) + NSYM * 2 + (size_t)W3_WARPS * (W3_WIN + 8) * 2;
 
 // ---- planes ------------------------------------------------------------------------------------
 // (sym << 8) | len of the code word that is a prefix of the left-aligned window, from t1 / t2; 0 when
@@ -134,14 +137,14 @@ int launch_table_planes(Ctx *c, DecodeTable *d_tab)
     return HF_OK;
 }
 
-// length of the code word at the head of `win` from a micro-tree entry e (bit 0 set)
+// length of the code word at the head of `win` from a micro-tree entry e (bit 0 set); b = slot of the next 4 bits
 __device__ __forceinline__ uint32_t micro_len(uint32_t e, uint32_t b)
 {
-    const uint32_t mask = e & 0xFFFFu;
-    const uint32_t y = mask << (31 - b);                // leaf starts at or below slot b, slot b in bit 31
-    const uint32_t x = (mask | 0x10000u) >> (b + 1);    // leaf starts above slot b, sentinel at slot 16
-    const uint32_t size = __clz(y) + __ffs(x);          // slots of the leaf that holds b: 1, 2, 4, 8 or 16
-    return __clz(size) - (31 - MICRO_MAX);              // MICRO_MAX - log2(size)
+    const uint32_t low = (2u << b) - 1u;                        // slots 0 .. b
+    const uint32_t m = e & 0xFFFFu;
+    const uint32_t s = 31u - __clz(m & low);                    // slot where the leaf that holds b starts
+    const uint32_t nx = __ffs((m | 0x10000u) & ~low) - 1u;      // slot where the next leaf starts (16 = none)
+    return __clz(nx - s) - (31u - MICRO_MAX);                   // MICRO_MAX - log2(leaf slots)
 }
 __device__ __forceinline__ uint32_t micro_slot(uint32_t win) { return (win >> (32 - MICRO_MAX)) & ((1u << MICRO_D) - 1u); }
 __device__ __forceinline__ uint32_t micro_leaf(uint32_t e, uint32_t b)
@@ -404,70 +407,80 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
 }
 
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(W2_THREADS, 1)
-dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+// Every WARP works on its own: a unit of 32 consecutive subsequences (1 KiB of payload), whose output offset
+// it derives itself from the chunk's records (no CTA-wide scan, no CTA barrier after the planes are loaded).
+// The symbols of a unit are compacted in the warp's staging window and leave with aligned 128-bit stores.
+__global__ void __launch_bounds__(W3_THREADS, 1)
+dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                   unsigned long long n_symbols, uint16_t *__restrict__ out, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
-    extern __shared__ __align__(16) uint32_t w2_smem[];
-    uint32_t *s_t14 = w2_smem;                                                  // 2^MICRO_K
+    extern __shared__ __align__(16) uint32_t w3_smem[];
+    uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
     uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
-    uint16_t *sout = s_leaves + NSYM;                                           // W2_WIN + 8
-    __shared__ uint32_t s_w[33];
     if (tab->single_sym) return;
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint16_t *sout = s_leaves + NSYM + wid * (W3_WIN + 8);                      // this warp's window
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
-        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W2_THREADS) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
         src = reinterpret_cast<const uint4 *>(tab->leaves);
         dst = reinterpret_cast<uint4 *>(s_leaves);
-        for (uint32_t i = tid; i < NSYM * 2 / 16; i += W2_THREADS) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < NSYM * 2 / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
     }
+    __syncthreads();
     const uint32_t k2shift = 32u - tab->k2;
-    const uint32_t sub0 = tid * SUB_BITS;
     uint32_t bad = 0;
+    constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
+    const unsigned long long nunits = nch * UPC;
 
-    for (unsigned long long c = blockIdx.x; c < nch; c += gridDim.x) {
-        __syncthreads();                                // planes loaded / sout, s_w reuse
-        const unsigned long long base = L.chunkBase[c];
-        if (base >= n_symbols) continue;                // uniform over the CTA
-        const uint32_t inf = L.info[c * DEC_THREADS + tid];
+    for (unsigned long long ug = (unsigned long long)blockIdx.x * W3_WARPS + wid; ug < nunits;
+         ug += (unsigned long long)gridDim.x * W3_WARPS) {
+        const unsigned long long c = ug / UPC;
+        const uint32_t u = (uint32_t)(ug % UPC);
+        const unsigned long long cbase = L.chunkBase[c];
+        if (cbase >= n_symbols) continue;
+        // symbols of the chunk before my unit: lane l sums the 16 records [16 l, 16 l + 16) of the chunk
+        uint32_t before;
+        {
+            const uint4 *ip = reinterpret_cast<const uint4 *>(L.info + c * DEC_THREADS);
+            const uint4 a = ip[2 * lane], d = ip[2 * lane + 1];
+            const uint32_t w8[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sum += ((w8[i] & 0xFFFFu) >> 6) + (w8[i] >> 22);
+            uint32_t x = (lane < 2 * u) ? sum : 0u;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            before = x;
+        }
+        const uint32_t t = 32 * u + lane;               // my subsequence of the chunk
+        const uint32_t inf = L.info[c * DEC_THREADS + t];
         const uint32_t cnt = inf >> 6;
-        uint32_t pos = (c == 0 && tid == 0) ? (uint32_t)F0 : (inf & 63u);   // the stream head may sit past bit 63
-        uint32_t r[9];
-        load_sub(r, frame, frame_bytes, c, tid, lane);
-
-        // exclusive scan of the counts over the chunk
+        uint32_t pos = (c == 0 && t == 0) ? (uint32_t)F0 : (inf & 63u);     // the stream head may sit past bit 63
         uint32_t x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_w[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            const uint32_t sv = lane < W2_THREADS / 32 ? s_w[lane] : 0u;
-            uint32_t v = sv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += y; }
-            if (lane < W2_THREADS / 32) s_w[lane] = v - sv;
-            if (lane == 31) s_w[32] = v;
-        }
-        __syncthreads();
-        const uint32_t off = x - cnt + s_w[wid];        // chunk-relative index of my first symbol
-        unsigned long long total = s_w[32];
+        const uint32_t off = x - cnt;                   // unit-relative index of my first symbol
+        unsigned long long total = __shfl_sync(0xFFFFFFFFu, x, 31);
+        const unsigned long long base = cbase + before;
+        if (base >= n_symbols) continue;
         if (base + total > n_symbols) total = n_symbols - base;   // garbage past the payload end is dropped
         const uint32_t my_end = (uint32_t)min((unsigned long long)(off + cnt), total);
-        uint32_t o = off;                               // chunk-relative index of my next symbol
+        uint32_t o = off;                               // unit-relative index of my next symbol
+        uint32_t r[9];
+        load_sub(r, frame, frame_bytes, c, t, lane);
 
         const uint32_t mis = (uint32_t)(base & 7);      // staging slot j <-> output symbol base - mis + j
-        for (unsigned long long w0 = 0; w0 < total; w0 += W2_WIN) {
-            const uint32_t wend = (uint32_t)min(total, w0 + W2_WIN);
+        for (uint32_t w0 = 0; w0 < (uint32_t)total; w0 += W3_WIN) {
+            const uint32_t wend = min((uint32_t)total, w0 + W3_WIN);
             const uint32_t o_end = min(my_end, wend);
             if (o < o_end) {
-                uint16_t *sp = sout + (o - (uint32_t)w0 + mis);
-                uint16_t *const sp_end = sout + (o_end - (uint32_t)w0 + mis);
+                uint16_t *sp = sout + (o - w0 + mis);
+                uint16_t *const sp_end = sout + (o_end - w0 + mis);
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
                     const uint32_t lw = 32u * (w + 1);
@@ -485,7 +498,7 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                             if (len == 0) {
                                 uint32_t e = __ldg(tab->flat2 + (win >> k2shift));
                                 if (e == 0) {
-                                    e = slow_decode(tab, frame, frame_bytes, c * CHUNK_BITS + sub0 + pos);
+                                    e = slow_decode(tab, frame, frame_bytes, c * CHUNK_BITS + t * SUB_BITS + pos);
                                     bad |= e >> 31;
                                 }
                                 len = e & 0x7Fu;
@@ -498,12 +511,12 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                 }
                 o = o_end;
             }
-            __syncthreads();
+            __syncwarp();
             // flush [w0, wend): staging slots [mis, mis + n)
-            const uint32_t n = wend - (uint32_t)w0;
+            const uint32_t n = wend - w0;
             uint16_t *dst = out + base + w0 - mis;      // 16-byte aligned when out is
             const uint32_t nvec = (mis + n + 7) / 8;
-            for (uint32_t q = tid; q < nvec; q += W2_THREADS) {
+            for (uint32_t q = lane; q < nvec; q += 32) {
                 const uint32_t j0 = q * 8;
                 if (j0 >= mis && j0 + 8 <= mis + n && (((uintptr_t)(dst + j0) & 15) == 0)) {
                     st_stream_v4(dst + j0, reinterpret_cast<const uint4 *>(sout)[q]);
@@ -512,7 +525,7 @@ dec_write2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         if (j >= mis && j < mis + n) dst[j] = sout[j];
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
@@ -681,13 +694,13 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
 {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         attr = true;
     }
-    unsigned long long grid = nch;
+    unsigned long long grid = (nch * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    HF_PROF(c, "dec_write2_kernel");
-    dec_write2_kernel<<<(unsigned)grid, W2_THREADS, W2_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out, gate);
+    HF_PROF(c, "dec_write3_kernel");
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out, gate);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
