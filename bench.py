@@ -203,11 +203,12 @@ def run_reference(args):
 KERNEL_BYTES = {
     # algorithmic bytes of one launch as a function of (N shard bytes, C shard bytes): DESIGN.md "Kernels"
     "hist_smem_kernel": lambda n, c: n,
-    "encode_kernel<false>": lambda n, c: n + c,
-    "encode_kernel<true>": lambda n, c: n + c,
-    "dec_sync_kernel": lambda n, c: c,
+    "enc_count_kernel": lambda n, c: n,
+    "encode_kernel": lambda n, c: n + c,
+    "dec_sync3_kernel": lambda n, c: c,
+    "dec_write3_kernel": lambda n, c: c + n,
+    "dec_sync_kernel": lambda n, c: c,          # HF_DECODE_OLD=1: the first-generation kernels
     "dec_write_kernel": lambda n, c: c + n,
-    "decode_kernel": lambda n, c: c + n,
 }
 
 

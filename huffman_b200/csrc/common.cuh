@@ -90,6 +90,10 @@ struct DecodeTable {
     uint32_t pad2[3];
     alignas(16) uint32_t t14[1u << MICRO_K];
     alignas(16) uint16_t leaves[NSYM];
+    // d14: what the synchronisation walks need of t14 (lengths only): (len << 4) | 0xC for a code of at most 14 bits
+    // (0xC alone: not here), else the micro tree as 16 two-bit fields, field j = (length at slot j) - 15.  A micro tree
+    // never has the low nibble 0xC: slot 0 at depth 1 covers slot 1 as well.
+    alignas(16) uint32_t d14[1u << MICRO_K];
     alignas(16) uint16_t micro_sym[16u << MICRO_K];     // build scratch: symbol at every slot of every prefix
     alignas(16) uint8_t lenflat[1u << FLAT_MAX];
     alignas(16) uint32_t flat2[1u << FLAT_MAX];

@@ -65,11 +65,12 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
         // entry of the 14-bit prefix i: a short code, or the shape of the micro tree below it
         const uint32_t w0 = i << (32 - MICRO_K);
         const uint32_t e0 = lookup_win32(tab, w0);
-        uint32_t entry = 0;
+        uint32_t entry = 0, dw = 0xCu;
         if (e0 && (e0 & 0x7Fu) <= MICRO_K) {
             entry = ((e0 >> 8) << 16) | ((e0 & 0x7Fu) << 1);
+            dw = ((e0 & 0x7Fu) << 4) | 0xCu;
         } else {
-            uint32_t mask = 0;
+            uint32_t mask = 0, depths = 0;
             bool ok = true;
             for (uint32_t j = 0; j < (1u << MICRO_D); j++) {
                 const uint32_t e = lookup_win32(tab, w0 | (j << (32 - MICRO_MAX)));
@@ -77,10 +78,12 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
                 if (e == 0 || len <= MICRO_K || len > MICRO_MAX) { ok = false; break; }
                 tab->micro_sym[i * (1u << MICRO_D) + j] = (uint16_t)(e >> 8);
                 if ((j & ((1u << (MICRO_MAX - len)) - 1u)) == 0) mask |= 1u << j;       // first slot of its leaf
+                depths |= (len - MICRO_K - 1u) << (2 * j);
             }
-            if (ok) entry = mask;                       // the base comes from dt_micro_kernel
+            if (ok) { entry = mask; dw = depths; }      // the base comes from dt_micro_kernel
         }
         tab->t14[i] = entry;
+        tab->d14[i] = dw;
     }
     if (i < (1u << k2)) {
         const uint32_t e = lookup_win32(tab, i << (32 - k2));
@@ -245,12 +248,12 @@ __device__ __forceinline__ void walk_span(const uint32_t *row, const uint32_t *s
         while (pos < lw) {
             const uint32_t *wp = row + (pos >> 5);
             const uint32_t win = __funnelshift_l(wp[1], wp[0], pos);
-            const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
+            const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];         // the d14 plane
             uint32_t len;
-            if (e14 & 1u) {
-                len = micro_len(e14, micro_slot(win));
+            if ((e14 & 0xFu) != 0xCu) {
+                len = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);   // micro tree: 2 bits per slot
             } else {
-                len = (e14 >> 1) & 0x7Fu;
+                len = e14 >> 4;
                 if (len == 0) {
                     len = __ldg(tab->lenflat + (win >> k2shift));
                     if (len == 0) {
@@ -304,7 +307,7 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);       // lengths only
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
     }

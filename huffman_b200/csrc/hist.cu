@@ -23,12 +23,13 @@ constexpr uint64_t HIST_SMALL_BYTES = 1u << 18;
 
 __device__ __forceinline__ uint32_t fold(uint32_t sym) { return sym ^ (sym >> 8); }   // involution on 16 bits
 
-__device__ __forceinline__ void count_sym(uint32_t *sh, unsigned long long *ghist, uint32_t sym)
+// adds n (< 0x2000) to the bin of `sym`
+__device__ __forceinline__ void count_sym(uint32_t *sh, unsigned long long *ghist, uint32_t sym, uint32_t n = 1)
 {
     uint32_t ix = fold(sym);
     uint32_t w = ix & 0x7FFFu;
     uint32_t sa = (ix >> 11) & 16u;                 // field select: 0 or 16
-    uint32_t inc = 1u << sa;
+    uint32_t inc = n << sa;
     uint32_t old = atomicAdd(&sh[w], inc);
     if (((old + inc) & ~old) & (0x8000u << sa)) {   // my add set bit 15 of the field
         atomicSub(&sh[w], 0x8000u << sa);
@@ -36,7 +37,29 @@ __device__ __forceinline__ void count_sym(uint32_t *sh, unsigned long long *ghis
     }
 }
 
-__device__ __forceinline__ void count_vec(uint32_t *sh, unsigned long long *ghist, const uint4 &v)
+// Warp aggregation of the hot bin: atomics of lanes that hit the SAME shared-memory word serialise, and skewed
+// inputs (text, Zipf, two-valued data) send most lanes to one bin.  The first symbol of lane 0 is taken as the
+// warp's candidate: its occurrences in the 256 symbols of this step are counted in registers and added with ONE
+// atomic; everything else goes bin by bin.  A candidate that pays (>= ~10 % of the symbols) is kept for the next
+// steps; otherwise the warp counts bin by bin for 15 steps and then tries the symbol it meets first.
+// Returns how often the candidate occurred (warp-wide), so the caller can stop trying on flat inputs.
+__device__ __forceinline__ uint32_t count_vec(uint32_t *sh, unsigned long long *ghist, const uint4 &v, uint32_t hot)
+{
+    const uint32_t s[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                           v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+    uint32_t nh = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) nh += (s[j] == hot);
+    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, nh);
+    if ((threadIdx.x & 31) == 0) count_sym(sh, ghist, hot, tot);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (s[j] != hot) count_sym(sh, ghist, s[j]);
+    return tot;
+}
+
+// the same bin by bin, for the lanes of a partly filled warp
+__device__ __forceinline__ void count_vec_partial(uint32_t *sh, unsigned long long *ghist, const uint4 &v)
 {
     count_sym(sh, ghist, v.x & 0xFFFFu); count_sym(sh, ghist, v.x >> 16);
     count_sym(sh, ghist, v.y & 0xFFFFu); count_sym(sh, ghist, v.y >> 16);
@@ -55,15 +78,27 @@ hist_smem_kernel(const uint4 *__restrict__ in, uint64_t n_vec, uint32_t *__restr
 
     const uint64_t step = (uint64_t)gridDim.x * HIST_THREADS * HIST_UNROLL;
     uint64_t i = (uint64_t)blockIdx.x * HIST_THREADS * HIST_UNROLL + threadIdx.x;
-    for (; i + (HIST_UNROLL - 1) * HIST_THREADS < n_vec; i += step) {
+    const uint32_t lane = threadIdx.x & 31;         // whole warps only: count_vec uses warp-wide operations
+    uint32_t skip = 0;                              // steps for which this warp does not try to aggregate
+    uint32_t hot = 0x10000u;                        // the warp's candidate symbol (none yet)
+    for (; (i - lane) + 31 + (HIST_UNROLL - 1) * HIST_THREADS < n_vec; i += step) {
         uint4 v[HIST_UNROLL];
 #pragma unroll
         for (int j = 0; j < HIST_UNROLL; j++) v[j] = ld_stream_v4(in + i + j * HIST_THREADS);
+        if (skip == 0) {
+            if (hot > 0xFFFFu) hot = __shfl_sync(0xFFFFFFFFu, v[0].x & 0xFFFFu, 0);
+            uint32_t hits = 0;
 #pragma unroll
-        for (int j = 0; j < HIST_UNROLL; j++) count_vec(sh, ghist, v[j]);
+            for (int j = 0; j < HIST_UNROLL; j++) hits += count_vec(sh, ghist, v[j], hot);
+            if (hits < HIST_UNROLL * 24) { skip = 15; hot = 0x10000u; }    // under ~10 % of the symbols: not worth it
+        } else {
+            skip--;
+#pragma unroll
+            for (int j = 0; j < HIST_UNROLL; j++) count_vec_partial(sh, ghist, v[j]);
+        }
     }
-    for (; i < n_vec; i += HIST_THREADS)            // ragged end of this CTA's last strip
-        if (i < n_vec) count_vec(sh, ghist, ld_stream_v4(in + i));
+    for (; i < n_vec; i += HIST_THREADS)            // ragged end of this CTA's last strip, bin by bin
+        count_vec_partial(sh, ghist, ld_stream_v4(in + i));
     __syncthreads();
 
     uint4 *dst = reinterpret_cast<uint4 *>(partials + (size_t)blockIdx.x * HIST_WORDS);
