@@ -488,8 +488,8 @@ encode_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebo
     }
 }
 
-int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
-                  uint64_t start_bit, uint32_t maxlen_hint)
+int launch_encode_old(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
+                      uint64_t start_bit, uint32_t maxlen_hint)
 {
     (void)maxlen_hint;
     const uint64_t n_sym = n_bytes / 2;

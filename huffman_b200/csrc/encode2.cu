@@ -1,0 +1,565 @@
+// encode2.cu — warp-independent Huffman encoder (the default; encode.cu keeps the first, CTA-tiled version
+// behind HF_ENCODE_OLD=1 for A/B timing).
+//
+// Replaces populateCWLength + thrust::transform_inclusive_scan + encodeFromCW + the host tail flush
+// (/root/reference/Compressor.cu:50-74, :152-313, :541-601, :673-684): the reference materialises 12 bytes of
+// scratch per symbol and binary-searches the offsets once per OUTPUT byte.
+//
+// Work is cut into UNITS of 512 symbols (1 KiB of input, 16 symbols per lane) and GROUPS of 32 units.
+//   enc_bits_kernel     bits of every unit (u32) and of every group, from the 64 KiB length plane in shared
+//                       memory.  Reads N, writes N / 256.
+//   enc_scan*_kernel    exclusive scan of the group totals (two tiny launches).
+//   encode2_kernel      one persistent CTA per SM, 24 warps, the 192 KiB code table (24-bit entries in two planes,
+//                       index XOR-folded against bank conflicts) in shared memory.  Every WARP packs groups on its
+//                       own: unit start = group start + a shuffle scan of the 32 unit counts; the lanes look their
+//                       16 codes up, a shuffle scan of the lane totals gives the lane's bit offset, pairs of codes
+//                       are merged in registers and OR-ed into the warp's zeroed staging window (predicated
+//                       red.shared, no divergence), and the window leaves with aligned 128-bit stores.  A 32-bit
+//                       word belongs to the unit that holds its first bit: the owner completes its last, partial
+//                       word by encoding the symbols that FOLLOW the unit, so units exchange nothing and there is
+//                       no CTA barrier after the table is loaded.  Reads N, writes C.
+// Codes longer than 23 bits (not in the shared table) and units whose bits exceed the staging window take a
+// slow per-symbol path through the global codebook.
+// Bits before the start phase in the first byte are preserved (they belong to the header or to the previous shard,
+// C:541, C:294-310); the last byte is zero padded (C:597-601).
+//
+// Algorithmic bytes: N read + C written (traffic 2N + C + N/128).  Roofline: HBM; today issue / LSU bound.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace hf {
+
+constexpr uint32_t UNIT_SYMS = 512;
+constexpr uint32_t GROUP_UNITS = 32;
+constexpr uint32_t GROUP_SYMS = UNIT_SYMS * GROUP_UNITS;            // 16,384
+constexpr int BITS_THREADS = 512;
+constexpr int E2_WARPS = 24;
+constexpr int E2_THREADS = E2_WARPS * 32;
+constexpr uint32_t E2_PLANE_BYTES = NSYM * 3;                       // p16 + p8
+constexpr uint32_t E2_WIN = 372;                                    // staging words per warp (multiple of 4)
+constexpr size_t E2_SMEM = E2_PLANE_BYTES + (size_t)E2_WARPS * E2_WIN * 4;
+constexpr uint32_t SCAN_PER_BLOCK = 4096;                           // groups per block of the first scan kernel
+constexpr unsigned long long NOT_FINAL = ~0ull;
+
+__device__ __forceinline__ uint32_t fold16(uint32_t sym) { return sym ^ (sym >> 8); }      // involution on 16 bits
+
+struct Enc2Work {                       // device arrays in ctx->ws
+    uint32_t *unit_bits;                // [ngroups * 32]
+    uint32_t *group_bits;               // [ngroups]
+    unsigned long long *group_start;    // [ngroups]  exclusive inside its scan block
+    unsigned long long *block_start;    // [nblocks]  exclusive over the scan blocks
+};
+
+// the 16 symbols of lane `lane` of unit `unit`; 0x10000 = no symbol (past the end)
+__device__ __forceinline__ void load_unit(const uint8_t *in_bytes, uint64_t n_sym, bool aligned, uint64_t unit, uint32_t lane,
+                                          uint32_t (&sym)[16])
+{
+    const uint64_t s0 = unit * UNIT_SYMS + lane * 16;
+    if (aligned && s0 + 16 <= n_sym) {
+        const uint4 a = ld_stream_v4(in_bytes + s0 * 2), b = ld_stream_v4(in_bytes + s0 * 2 + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) { sym[2 * i] = w[i] & 0xFFFFu; sym[2 * i + 1] = w[i] >> 16; }
+    } else {
+        const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
+#pragma unroll
+        for (int j = 0; j < 16; j++) sym[j] = s0 + j < n_sym ? (uint32_t)in16[s0 + j] : 0x10000u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BITS_THREADS)
+enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, Enc2Work W,
+                uint64_t ngroups)
+{
+    extern __shared__ __align__(16) uint8_t s_len[];           // lenf plane, 64 KiB
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cb->lenf);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_len);
+        for (uint32_t i = tid; i < NSYM / 16; i += BITS_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const uint64_t warp0 = (uint64_t)blockIdx.x * (BITS_THREADS / 32) + (tid >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (BITS_THREADS / 32);
+    for (uint64_t g = warp0; g < ngroups; g += nwarps) {
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (uint32_t u = 0; u < GROUP_UNITS; u++) {
+            const uint64_t unit = g * GROUP_UNITS + u;
+            uint32_t t = 0;
+            if (unit * UNIT_SYMS < n_sym) {
+                uint32_t sym[16];
+                load_unit(in_bytes, n_sym, aligned, unit, lane, sym);
+#pragma unroll
+                for (int j = 0; j < 16; j++) t += sym[j] > 0xFFFFu ? 0u : (uint32_t)s_len[fold16(sym[j])];
+                t = __reduce_add_sync(0xFFFFFFFFu, t);
+            }
+            if (lane == u) mine = t;
+        }
+        W.unit_bits[g * GROUP_UNITS + lane] = mine;
+        const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, mine);
+        if (lane == 0) W.group_bits[g] = tot;
+    }
+}
+
+// exclusive scan of group_bits inside blocks of SCAN_PER_BLOCK groups; block totals to block_start (scanned next)
+__global__ void __launch_bounds__(1024)
+enc_scan1_kernel(Enc2Work W, uint64_t ngroups)
+{
+    __shared__ unsigned long long s_w[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr uint32_t PER = SCAN_PER_BLOCK / 1024;
+    const uint64_t g0 = (uint64_t)blockIdx.x * SCAN_PER_BLOCK + tid * PER;
+    uint32_t v[PER];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) { v[j] = g0 + j < ngroups ? W.group_bits[g0 + j] : 0u; sum += v[j]; }
+    unsigned long long x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned long long s = s_w[lane];
+        unsigned long long t = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        s_w[lane] = t - s;
+        if (lane == 31) s_w[32] = t;
+    }
+    __syncthreads();
+    unsigned long long run = x - sum + s_w[wid];
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) { if (g0 + j < ngroups) W.group_start[g0 + j] = run; run += v[j]; }
+    if (tid == 0) W.block_start[blockIdx.x] = s_w[32];
+}
+
+// exclusive scan of the block totals, in place (one CTA; a 180 GB input has ~1,400 blocks)
+__global__ void __launch_bounds__(1024)
+enc_scan2_kernel(Enc2Work W, uint32_t nblocks)
+{
+    __shared__ unsigned long long s_w[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (nblocks + 1023) / 1024;
+    const uint32_t lo = min(nblocks, tid * per), hi = min(nblocks, (tid + 1) * per);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += W.block_start[i];
+    unsigned long long x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned long long s = s_w[lane];
+        unsigned long long t = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        s_w[lane] = t - s;
+    }
+    __syncthreads();
+    unsigned long long run = x - sum + s_w[wid];
+    for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = W.block_start[i]; W.block_start[i] = run; run += v; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// predicated shared-memory OR without a branch
+__device__ __forceinline__ void red_or_if(bool p, uint32_t saddr, uint32_t v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.shared.or.b32 [%1], %2;\n\t}"
+                 :: "r"((uint32_t)p), "r"(saddr), "r"(v) : "memory");
+}
+
+// (len, code) of one symbol from the shared planes, or from the global codebook when it is not there
+__device__ __forceinline__ void lookup_any(const uint16_t *p16, const uint8_t *p8, const Codebook *cb, uint32_t sym,
+                                           uint32_t &len, unsigned long long &code)
+{
+    const uint32_t f = fold16(sym);
+    const uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
+    if (x) { len = 31 - __clz(x); code = x ^ (1u << len); }
+    else { len = cb->len[sym]; code = cb->code[sym]; }
+}
+
+// OR `len` bits of `code` (right aligned) into the window at window bit `pos`; words outside [0, E2_WIN) of the
+// window that starts at window word `wbase` are dropped.  Any length up to 64.
+__device__ __forceinline__ void put_code_slow(uint32_t sbase, uint32_t wbase, uint32_t pos, unsigned long long code,
+                                              uint32_t len)
+{
+    while (len) {
+        const uint32_t w = pos >> 5, sh = pos & 31;
+        const uint32_t take = min(len, 32u - sh);
+        const uint32_t bits = (uint32_t)(code >> (len - take)) & (take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u));
+        const uint32_t i = w - wbase;
+        if (i < E2_WIN) red_or_if(true, sbase + 4u * i, bits << (32 - sh - take));
+        pos += take;
+        len -= take;
+    }
+}
+
+// what a warp needs to pack a unit
+struct UnitCtx {
+    const uint8_t *in_bytes;
+    uint64_t n_sym, nunits;
+    const Codebook *cb;
+    const uint16_t *p16;
+    const uint8_t *p8;
+    uint32_t *stage;
+    uint32_t sbase;
+    uint8_t *frame;
+    unsigned long long bit0;
+    bool aligned;
+};
+
+// One unit the general way: ragged or unaligned input, the stream head and tail, codes longer than 23 bits, units
+// whose bits exceed the staging window.  (The common case is inlined in the kernel.)
+__device__ __noinline__ void encode_unit_general(const UnitCtx &C, uint64_t unit, uint32_t bits, unsigned long long gbit,
+                                                 uint32_t lane)
+{
+    const uint16_t *p16 = C.p16;
+    const uint8_t *p8 = C.p8;
+    const Codebook *cb = C.cb;
+    uint32_t *stage = C.stage;
+    const uint32_t sbase = C.sbase;
+    uint8_t *frame = C.frame;
+    uint32_t *gw = reinterpret_cast<uint32_t *>(frame);
+    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(C.in_bytes);
+    const uint64_t n_sym = C.n_sym;
+    const unsigned long long bit0 = C.bit0;
+
+    const unsigned long long gend = gbit + bits;
+    const uint32_t phase = (uint32_t)(gbit & 127);
+    const unsigned long long G0 = (gbit - phase) >> 5;      // frame word of window word 0 (multiple of 4)
+    const bool head = unit == 0, last_unit = unit + 1 == C.nunits;
+    const uint32_t own_lo = head ? (phase >> 5) : ((phase + 31) >> 5);
+    const uint32_t end_rel = phase + bits;                  // window bit after my last bit
+    const uint32_t own_hi = (end_rel - 1) >> 5;             // bits > 0 here
+
+    uint32_t sym[16];
+    load_unit(C.in_bytes, n_sym, C.aligned, unit, lane, sym);
+    uint32_t L = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) L += sym[j] > 0xFFFFu ? 0u : (uint32_t)cb->len[sym[j]];
+    uint32_t off = L;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, o); if (lane >= o) off += y; }
+    off -= L;                                               // unit bits before my first symbol
+
+    const uint32_t npass = own_hi / E2_WIN + 1;
+    for (uint32_t pass = 0; pass < npass; pass++) {
+        const uint32_t wbase = pass * E2_WIN;
+        const uint32_t used = min(E2_WIN, own_hi + 1 - wbase);         // words of the window that will be used
+        for (uint32_t i = lane; i < (used + 3) / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        {
+            uint32_t pos = phase + off;
+#pragma unroll 1
+            for (int j = 0; j < 16; j++) {
+                uint32_t sj = sym[0];
+#pragma unroll
+                for (int k = 1; k < 16; k++) sj = (k == j) ? sym[k] : sj;  // register select: sym[] stays out of local memory
+                if (sj > 0xFFFFu) continue;
+                uint32_t len;
+                unsigned long long code;
+                lookup_any(p16, p8, cb, sj, len, code);
+                put_code_slow(sbase, wbase, pos, code, len);
+                pos += len;
+            }
+        }
+        __syncwarp();
+
+        // ---- the stream head and my last, partial word (lane 0) ----
+        const bool last_pass = pass + 1 == npass;
+        unsigned long long fin = NOT_FINAL;
+        if (lane == 0) {
+            if (pass == 0 && head) {
+                // preserve the bits of the first byte that precede the start phase
+                const uint32_t b = frame[gbit >> 3];
+                const uint32_t keep = b & ~(0xFFu >> (gbit & 7));
+                stage[phase >> 5] |= keep << (24 - 8 * (uint32_t)((gbit >> 3) & 3));
+            }
+            if (last_pass) {
+                if (last_unit) fin = gend;
+                uint32_t have = end_rel & 31;               // bits of my last word that are mine
+                if (have && !last_unit) {
+                    // complete the word with the codes of the symbols that follow the unit
+                    uint32_t word = 0;
+                    uint64_t sx = (unit + 1) * UNIT_SYMS;
+                    unsigned long long end = gend;
+                    while (have < 32 && sx < n_sym) {
+                        uint32_t len;
+                        unsigned long long code;
+                        lookup_any(p16, p8, cb, in16[sx], len, code);
+                        if (len) {
+                            const unsigned long long left = code << (64 - len);    // left aligned
+                            word |= (uint32_t)(left >> 32) >> have;
+                            have += len;
+                            end += len;
+                        }
+                        sx++;
+                    }
+                    stage[own_hi - wbase] |= word;
+                    if (have < 32) fin = end;               // the input ended inside my word: it is the last one
+                }
+            }
+        }
+        fin = __shfl_sync(0xFFFFFFFFu, fin, 0);
+        __syncwarp();
+
+        // ---- my words of this window leave: 128-bit stores where a whole group is mine, else words / bytes ----
+        const unsigned long long W0 = G0 + wbase;
+        const uint32_t hi_here = min(own_hi, wbase + E2_WIN - 1) - wbase;      // last window word to store
+        const uint32_t lo_here = own_lo > wbase ? own_lo - wbase : 0u;
+        for (uint32_t q = (lo_here >> 2) + lane; q <= (hi_here >> 2); q += 32) {
+            uint4 o = reinterpret_cast<const uint4 *>(stage)[q];
+            o.x = bswap32(o.x); o.y = bswap32(o.y); o.z = bswap32(o.z); o.w = bswap32(o.w);
+            const uint32_t w0 = 4 * q;                      // window word of o.x
+            const bool whole = w0 >= lo_here && w0 + 3 <= hi_here && !(head && pass == 0 && w0 <= (phase >> 5)) &&
+                               !(fin != NOT_FINAL && w0 + 3 + wbase >= own_hi);
+            if (whole) {
+                st_stream_v4(gw + W0 + w0, o);
+            } else {
+                const uint32_t vv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t wk = w0 + k;
+                    if (wk < lo_here || wk > hi_here) continue;
+                    const unsigned long long fw = W0 + wk;      // frame word
+                    uint32_t b_lo = 0, b_hi = 4;                // byte range [b_lo, b_hi) of this word to store
+                    if (fw == (bit0 >> 5)) b_lo = (uint32_t)((bit0 >> 3) & 3);         // bytes before the stream are not ours
+                    if (fin != NOT_FINAL && wk + wbase == own_hi) b_hi = (uint32_t)(((fin - 1) >> 3) & 3) + 1;   // bytes holding bits
+                    if (b_lo == 0 && b_hi == 4) gw[fw] = vv[k];
+                    else
+                        for (uint32_t b = b_lo; b < b_hi; b++)
+                            frame[fw * 4 + b] = (uint8_t)(vv[k] >> (8 * b));    // little-endian view of the swapped word
+                }
+            }
+        }
+        __syncwarp();                                       // the window is reused
+    }
+}
+
+__global__ void __launch_bounds__(E2_THREADS, 1)
+encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, uint8_t *stream,
+               uint64_t start_bit, Enc2Work W, uint64_t ngroups)
+{
+    extern __shared__ __align__(16) uint8_t e2_smem[];
+    const uint16_t *p16 = reinterpret_cast<const uint16_t *>(e2_smem);
+    const uint8_t *p8 = e2_smem + NSYM * 2;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(e2_smem + E2_PLANE_BYTES) + wid * E2_WIN;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cb->p16);
+        uint4 *dst = reinterpret_cast<uint4 *>(e2_smem);
+        for (uint32_t i = tid; i < E2_PLANE_BYTES / 16; i += E2_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    // aligned frame: bit 0 of the frame is the 16-byte boundary at or below `stream`
+    uint8_t *frame = reinterpret_cast<uint8_t *>((uintptr_t)stream & ~(uintptr_t)15);
+    uint32_t *gw = reinterpret_cast<uint32_t *>(frame);
+    const unsigned long long bit0 = ((uintptr_t)stream & 15) * 8ull + start_bit;   // first payload bit, frame coordinates
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const uint64_t nunits = (n_sym + UNIT_SYMS - 1) / UNIT_SYMS;
+    const UnitCtx C{in_bytes, n_sym, nunits, cb, p16, p8, stage, sbase, frame, bit0, aligned};
+
+    for (uint64_t g = (uint64_t)blockIdx.x * E2_WARPS + wid; g < ngroups; g += (uint64_t)gridDim.x * E2_WARPS) {
+        const unsigned long long gstart = bit0 + W.block_start[g / SCAN_PER_BLOCK] + W.group_start[g];
+        const uint32_t ub = W.unit_bits[g * GROUP_UNITS + lane];
+        uint32_t ux = ub;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ux, o); if (lane >= o) ux += y; }
+        ux -= ub;                                               // bits of the group before unit `lane`
+
+        uint4 cur0 = make_uint4(0, 0, 0, 0), cur1 = cur0;       // my 16 symbols of the unit at hand (when have_cur)
+        bool have_cur = false;
+        for (uint32_t u = 0; u < GROUP_UNITS; u++) {
+            const uint64_t unit = g * GROUP_UNITS + u;
+            if (unit >= nunits) break;
+            const uint32_t bits = __shfl_sync(0xFFFFFFFFu, ub, u);
+            const unsigned long long gbit = gstart + __shfl_sync(0xFFFFFFFFu, ux, u);  // unit's first bit, frame coordinates
+            const uint32_t phase = (uint32_t)(gbit & 127);
+            // words I own: those whose first bit is mine (the first unit also owns the word the stream starts in)
+            const uint32_t own_lo = unit == 0 ? (phase >> 5) : ((phase + 31) >> 5);
+            const uint32_t end_rel = phase + bits;                  // window bit after my last bit
+            const uint32_t own_hi = bits ? ((end_rel - 1) >> 5) : 0u;
+            if (!(bits > 0 && own_hi >= own_lo)) { have_cur = false; continue; }   // my bits sit in a word the unit before me completes
+
+            // the common case: whole units of an aligned input, this one and the next, away from the stream's ends
+            bool fast = aligned && unit != 0 && (unit + 2) * UNIT_SYMS <= n_sym && end_rel <= E2_WIN * 32;
+            uint32_t v[16];
+            uint32_t L = 0;
+            uint4 nxt0 = cur0, nxt1 = cur1;
+            if (fast) {
+                if (!have_cur) {
+                    const uint8_t *src = in_bytes + (unit * UNIT_SYMS + lane * 16) * 2;
+                    cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
+                }
+                {   // the next unit's symbols: prefetched for the next step, and lane 0 completes my last word with them
+                    const uint8_t *src = in_bytes + ((unit + 1) * UNIT_SYMS + lane * 16) * 2;
+                    nxt0 = ld_stream_v4(src); nxt1 = ld_stream_v4(src + 16);
+                }
+                const uint32_t w8[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+                uint32_t zero = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t sj = (j & 1) ? (w8[j >> 1] >> 16) : (w8[j >> 1] & 0xFFFFu);
+                    const uint32_t f = fold16(sj);
+                    const uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
+                    v[j] = x;
+                    zero = min(zero, x);
+                    L += 31 - __clz(x | 1u);
+                }
+                if (__any_sync(0xFFFFFFFFu, zero == 0)) fast = false;   // a code longer than 23 bits
+            }
+            if (!fast) {
+                encode_unit_general(C, unit, bits, gbit, lane);
+                have_cur = false;
+                continue;
+            }
+            uint32_t off = L;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, o); if (lane >= o) off += y; }
+            off -= L;                                               // unit bits before my first symbol
+
+            // ---- zero the window words that will be used, pack ----
+            for (uint32_t i = lane; i < (own_hi + 4) / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            {
+                uint32_t pos = phase + off;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const uint32_t x0 = v[j], x1 = v[j + 1];
+                    const uint32_t l0 = 31 - __clz(x0), l1 = 31 - __clz(x1);
+                    const uint32_t a32 = __funnelshift_lc(0u, x0, 32 - l0);   // left aligned, the leading one falls off
+                    const uint32_t b32 = __funnelshift_lc(0u, x1, 32 - l1);
+                    const uint32_t hi = a32 | (b32 >> l0);                    // l0 <= 23
+                    const uint32_t lo = __funnelshift_r(0u, b32, l0);
+                    const uint32_t LL = l0 + l1, sh = pos & 31;
+                    const uint32_t sa = sbase + 4u * (pos >> 5);
+                    red_or_if(LL != 0, sa, hi >> sh);
+                    red_or_if(sh + LL > 32, sa + 4, __funnelshift_r(lo, hi, sh));
+                    red_or_if(sh + LL > 64, sa + 8, __funnelshift_r(0u, lo, sh));
+                    pos += LL;
+                }
+            }
+            __syncwarp();
+            // ---- lane 0 completes my last, partial word with the codes that follow (the next unit's first symbols) ----
+            if (lane == 0) {
+                uint32_t have = end_rel & 31;                       // bits of my last word that are mine
+                if (have) {
+                    uint32_t word = 0;
+                    const uint32_t n8[8] = {nxt0.x, nxt0.y, nxt0.z, nxt0.w, nxt1.x, nxt1.y, nxt1.z, nxt1.w};
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if (have < 32) {
+                            const uint32_t sj = (j & 1) ? (n8[j >> 1] >> 16) : (n8[j >> 1] & 0xFFFFu);
+                            uint32_t len;
+                            unsigned long long code;
+                            lookup_any(p16, p8, cb, sj, len, code);
+                            if (len) {
+                                const unsigned long long left = code << (64 - len);    // left aligned
+                                word |= (uint32_t)(left >> 32) >> have;
+                                have += len;
+                            }
+                        }
+                    }
+                    // sixteen codes did not fill the word (one- and two-bit codes): go on from the input; the next
+                    // unit is whole, so the word does fill up before the input ends
+                    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
+                    for (uint64_t sx = (unit + 1) * UNIT_SYMS + 16; have < 32 && sx < n_sym; sx++) {
+                        uint32_t len;
+                        unsigned long long code;
+                        lookup_any(p16, p8, cb, in16[sx], len, code);
+                        if (len) {
+                            const unsigned long long left = code << (64 - len);
+                            word |= (uint32_t)(left >> 32) >> have;
+                            have += len;
+                        }
+                    }
+                    stage[own_hi] |= word;
+                }
+            }
+            __syncwarp();
+            // ---- my words leave: 128-bit stores where a whole group is mine, else single words ----
+            const unsigned long long G0 = (gbit - phase) >> 5;      // frame word of window word 0 (multiple of 4)
+            for (uint32_t q = (own_lo >> 2) + lane; q <= (own_hi >> 2); q += 32) {
+                uint4 o = reinterpret_cast<const uint4 *>(stage)[q];
+                o.x = bswap32(o.x); o.y = bswap32(o.y); o.z = bswap32(o.z); o.w = bswap32(o.w);
+                const uint32_t w0 = 4 * q;
+                if (w0 >= own_lo && w0 + 3 <= own_hi) {
+                    st_stream_v4(gw + G0 + w0, o);
+                } else {
+                    if (w0 >= own_lo && w0 <= own_hi) gw[G0 + w0] = o.x;
+                    if (w0 + 1 >= own_lo && w0 + 1 <= own_hi) gw[G0 + w0 + 1] = o.y;
+                    if (w0 + 2 >= own_lo && w0 + 2 <= own_hi) gw[G0 + w0 + 2] = o.z;
+                    if (w0 + 3 >= own_lo && w0 + 3 <= own_hi) gw[G0 + w0 + 3] = o.w;
+                }
+            }
+            __syncwarp();                                           // the window is reused
+            cur0 = nxt0; cur1 = nxt1;
+            have_cur = true;
+        }
+    }
+}
+
+int launch_encode_old(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
+                      uint64_t start_bit, uint32_t maxlen_hint);         // encode.cu
+
+int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
+                  uint64_t start_bit, uint32_t maxlen_hint)
+{
+    static int use_old = -1;
+    if (use_old < 0) { const char *e = getenv("HF_ENCODE_OLD"); use_old = (e && e[0] == '1') ? 1 : 0; }
+    if (use_old) return launch_encode_old(c, d_in, n_bytes, d_cb, d_stream, start_bit, maxlen_hint);
+
+    const uint64_t n_sym = n_bytes / 2;
+    if (n_sym == 0) return HF_OK;
+    if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
+    if ((uintptr_t)d_cb & 15) return set_err(c, HF_ERR_ARG, "hf_encode: codebook must be 16-byte aligned");
+    const uint64_t ngroups = (n_sym + GROUP_SYMS - 1) / GROUP_SYMS;
+    const uint64_t nblocks = (ngroups + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK;
+    if (nblocks > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_encode: input too large");
+    // the encode workspace sits behind the codebook workspace so the two never alias a live buffer
+    const size_t off = 8u << 20;
+    const size_t b_units = ((size_t)ngroups * GROUP_UNITS * 4 + 255) & ~(size_t)255;
+    const size_t b_gbits = ((size_t)ngroups * 4 + 255) & ~(size_t)255;
+    const size_t b_gstart = ((size_t)ngroups * 8 + 255) & ~(size_t)255;
+    const size_t b_blocks = ((size_t)nblocks * 8 + 255) & ~(size_t)255;
+    int rc = ensure_ws(c, off + b_units + b_gbits + b_gstart + b_blocks);
+    if (rc) return rc;
+    uint8_t *p = (uint8_t *)c->ws + off;
+    Enc2Work W;
+    W.unit_bits = reinterpret_cast<uint32_t *>(p); p += b_units;
+    W.group_bits = reinterpret_cast<uint32_t *>(p); p += b_gbits;
+    W.group_start = reinterpret_cast<unsigned long long *>(p); p += b_gstart;
+    W.block_start = reinterpret_cast<unsigned long long *>(p);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        HF_CUDA(c, cudaFuncSetAttribute(encode2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(enc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSYM));
+        attr_set = true;
+    }
+    // start_bit may exceed 8: fold whole bytes into the pointer
+    d_stream += start_bit >> 3;
+    start_bit &= 7;
+    const uint64_t bw = BITS_THREADS / 32;
+    uint64_t bgrid = (ngroups + bw - 1) / bw;
+    if (bgrid > (uint64_t)(3 * c->sm_count)) bgrid = 3 * c->sm_count;
+    HF_PROF(c, "enc_bits_kernel"); enc_bits_kernel<<<(unsigned)bgrid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "enc_scan1_kernel"); enc_scan1_kernel<<<(unsigned)nblocks, 1024, 0, c->stream>>>(W, ngroups);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "enc_scan2_kernel"); enc_scan2_kernel<<<1, 1024, 0, c->stream>>>(W, (uint32_t)nblocks);
+    HF_LAUNCH_CHECK(c);
+    uint64_t grid = (ngroups + E2_WARPS - 1) / E2_WARPS;
+    if (grid > (uint64_t)c->sm_count) grid = c->sm_count;
+    HF_PROF(c, "encode2_kernel"); encode2_kernel<<<(unsigned)grid, E2_THREADS, E2_SMEM, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, W, ngroups);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+}  // namespace hf

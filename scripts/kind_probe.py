@@ -32,8 +32,8 @@ for k in kinds:
     g = lambda nm: prof.get(nm, (1, 0.0))[1] / max(prof.get(nm, (1, 0.0))[0], 1)
     gs = lambda pre: sum(g(k) for k in prof if k.startswith(pre))
     dec = sum(g(k) for k in prof if k.startswith("dec") and not k.startswith("dec_parse") and not k.startswith("dec_entries"))
-    enc = g('encode_kernel') + g('enc_count_kernel')
+    enc = gs('encode') + (gs('enc_count') + gs('enc_bits') + gs('enc_scan'))
     print(f"{name:10s} ok={ok} ratio={img.numel() / n:.3f} maxlen={info.max_code_bits:2d} hist={g('hist_smem_kernel'):.3f} "
-          f"enc={enc:.3f} (count {g('enc_count_kernel'):.3f}) dec={dec:.3f} (sync {gs('dec_sync'):.3f} "
+          f"enc={enc:.3f} (count {(gs('enc_count') + gs('enc_bits') + gs('enc_scan')):.3f}) dec={dec:.3f} (sync {gs('dec_sync'):.3f} "
           f"fix {gs('dec_fix'):.3f} write {gs('dec_write'):.3f}) ms  "
           f"enc {(n + img.numel()) / enc / 1e6:.0f} GB/s dec {(n + img.numel()) / max(dec, 1e-9) / 1e6:.0f} GB/s", flush=True)

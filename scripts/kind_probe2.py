@@ -36,7 +36,7 @@ for k in os.environ.get("KINDS", "0,1,2,3,4,5").split(","):
     ok = bool(torch.equal(out[:n], d))
     g = lambda nm: prof.get(nm, (1, 0.0))[1] / max(prof.get(nm, (1, 0.0))[0], 1)
     gs = lambda pre: sum(g(k) for k in prof if k.startswith(pre))
-    print(f"{name:10s} ok={ok} bits/sym={bits / (n / 2):.2f} enc={g('encode_kernel'):.3f} count={g('enc_count_kernel'):.3f} "
+    print(f"{name:10s} ok={ok} bits/sym={bits / (n / 2):.2f} enc={gs('encode'):.3f} count={(gs('enc_count') + gs('enc_bits') + gs('enc_scan')):.3f} "
           f"sync={gs('dec_sync'):.3f} fix={gs('dec_fix'):.3f} write={gs('dec_write'):.3f} ms "
-          f"| per GiB: enc {1024 / mb * (g('encode_kernel') + g('enc_count_kernel')):.2f} sync {1024 / mb * gs('dec_sync'):.2f} "
+          f"| per GiB: enc {1024 / mb * (gs('encode') + (gs('enc_count') + gs('enc_bits') + gs('enc_scan'))):.2f} sync {1024 / mb * gs('dec_sync'):.2f} "
           f"write {1024 / mb * gs('dec_write'):.2f} ms", flush=True)
