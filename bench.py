@@ -203,7 +203,9 @@ def run_reference(args):
 KERNEL_BYTES = {
     # algorithmic bytes of one launch as a function of (N shard bytes, C shard bytes): DESIGN.md "Kernels"
     "hist_smem_kernel": lambda n, c: n,
-    "enc_count_kernel": lambda n, c: n,
+    "enc_bits_kernel": lambda n, c: n,
+    "encode2_kernel": lambda n, c: n + c,
+    "enc_count_kernel": lambda n, c: n,         # HF_ENCODE_OLD=1: the first-generation kernels
     "encode_kernel": lambda n, c: n + c,
     "dec_sync3_kernel": lambda n, c: c,
     "dec_write3_kernel": lambda n, c: c + n,

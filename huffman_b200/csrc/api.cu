@@ -112,6 +112,7 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     ok = ok && cudaMalloc(&c->d_cb, codebook_alloc_bytes()) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_tab, sizeof(DecodeTable)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_hist, NSYM * 8 + 256) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_scan, SCAN_BLOCKS_MAX * 8) == cudaSuccess;
     ok = ok && ensure_ws(c, 1) == HF_OK;
     if (!ok) { hf_ctx_destroy(reinterpret_cast<hf_ctx *>(c)); return HF_ERR_CUDA; }
     *out = reinterpret_cast<hf_ctx *>(c);
@@ -133,6 +134,7 @@ int hf_ctx_destroy(hf_ctx *ctx)
     if (c->d_cb) cudaFree(c->d_cb);
     if (c->d_tab) cudaFree(c->d_tab);
     if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_scan) cudaFree(c->d_scan);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->prof_ev) {
         for (uint32_t i = 0; i < 2 * PROF_CAP; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);

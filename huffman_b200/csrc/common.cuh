@@ -121,6 +121,7 @@ struct Ctx {
     void *d_cb;
     void *d_tab;
     void *d_hist;
+    void *d_scan;                   // block totals of the decoder's chunk scan (SCAN_BLOCKS_MAX u64)
     bool decode_exact_only;         // hf_set_decode_mode(1): skip the single-pass decoder (tests)
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
@@ -130,6 +131,7 @@ struct Ctx {
     const char **prof_name;         // PROF_CAP static strings
 };
 constexpr uint32_t PROF_CAP = 8192;
+constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload
 void prof_begin(Ctx *c, const char *name);
 void prof_end(Ctx *c);
 

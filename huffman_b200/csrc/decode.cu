@@ -523,30 +523,80 @@ __global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigne
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
-__global__ void __launch_bounds__(1024, 1)
-dec_scan_kernel(DecWork *work, unsigned long long nch, const unsigned long long *gate)
+// Exclusive scan of the chunk symbol counts -> chunkBase, in three small steps: every block of 4096 chunks scans
+// itself (dec_scan1_kernel), one CTA scans the block totals (dec_scan2_kernel), dec_scan3_kernel adds them back.
+constexpr uint32_t DSCAN_PER_BLOCK = 4096;
+
+__global__ void __launch_bounds__(1024)
+dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long *block_tot, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     __shared__ unsigned long long s_w[33];
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned long long per = (nch + 1023) / 1024;
-    const unsigned long long lo = min(nch, tid * per), hi = min(nch, (tid + 1) * per);
+    constexpr uint32_t PER = DSCAN_PER_BLOCK / 1024;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + tid * PER;
+    uint32_t v[PER];
     unsigned long long sum = 0;
-    for (unsigned long long i = lo; i < hi; i++) sum += L.chunkCnt[i];
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) { v[j] = i0 + j < nch ? L.chunkCnt[i0 + j] : 0u; sum += v[j]; }
     unsigned long long x = sum;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
     if (lane == 31) s_w[wid] = x;
     __syncthreads();
     if (wid == 0) {
         unsigned long long s = s_w[lane], t = s;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
         s_w[lane] = t - s;
+        if (lane == 31) s_w[32] = t;
     }
     __syncthreads();
     unsigned long long run = x - sum + s_w[wid];
-    for (unsigned long long i = lo; i < hi; i++) { L.chunkBase[i] = run; run += L.chunkCnt[i]; }
-    if (hi == nch && hi > lo) work->result[2] = run;     // symbols in the whole range
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) { if (i0 + j < nch) L.chunkBase[i0 + j] = run; run += v[j]; }
+    if (tid == 0) block_tot[blockIdx.x] = s_w[32];
+}
+
+__global__ void __launch_bounds__(1024)
+dec_scan2_kernel(DecWork *work, unsigned long long *block_tot, uint32_t nblocks, const unsigned long long *gate)
+{
+    if (gate && !(*gate & DF_GATE_MASK)) return;
+    __shared__ unsigned long long s_w[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (nblocks + 1023) / 1024;
+    const uint32_t lo = min(nblocks, tid * per), hi = min(nblocks, (tid + 1) * per);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += block_tot[i];
+    unsigned long long x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = s_w[lane], t = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        s_w[lane] = t - s;
+        if (lane == 31) work->result[2] = t;                // symbols in the whole range
+    }
+    __syncthreads();
+    unsigned long long run = x - sum + s_w[wid];
+    for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = block_tot[i]; block_tot[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(1024)
+dec_scan3_kernel(DecWork *work, unsigned long long nch, const unsigned long long *block_tot, const unsigned long long *gate)
+{
+    if (gate && !(*gate & DF_GATE_MASK)) return;
+    DecLayout L(work, nch);
+    const unsigned long long add = block_tot[blockIdx.x];
+    if (add == 0) return;
+    for (uint32_t j = threadIdx.x; j < DSCAN_PER_BLOCK; j += 1024) {
+        const unsigned long long i = (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + j;
+        if (i < nch) L.chunkBase[i] += add;
+    }
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -729,8 +779,17 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
         HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
     }
-    HF_PROF(c, "dec_scan_kernel"); dec_scan_kernel<<<1, 1024, 0, c->stream>>>(work, nch, gate);
-    HF_LAUNCH_CHECK(c);
+    {
+        const uint32_t nblocks = (uint32_t)((nch + DSCAN_PER_BLOCK - 1) / DSCAN_PER_BLOCK);
+        unsigned long long *block_tot = reinterpret_cast<unsigned long long *>(c->d_scan);
+        if (nblocks > SCAN_BLOCKS_MAX) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
+        HF_PROF(c, "dec_scan1_kernel"); dec_scan1_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, block_tot, gate);
+        HF_LAUNCH_CHECK(c);
+        HF_PROF(c, "dec_scan2_kernel"); dec_scan2_kernel<<<1, 1024, 0, c->stream>>>(work, block_tot, nblocks, gate);
+        HF_LAUNCH_CHECK(c);
+        HF_PROF(c, "dec_scan3_kernel"); dec_scan3_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, block_tot, gate);
+        HF_LAUNCH_CHECK(c);
+    }
     if (!old) return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16, gate);
     const size_t wsmem = (SW_PADDED + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
     static bool wattr = false;
