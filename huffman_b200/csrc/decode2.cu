@@ -210,12 +210,14 @@ __device__ __forceinline__ void load_sub(uint32_t (&r)[9], const uint8_t *frame,
 // one padded row of 33 words per thread (bank = (thread + word) mod 32; the pad word repeats the next
 // row's first word so a 32-bit window never leaves the row).
 constexpr int S3_THREADS = 1024;
+constexpr int TEAM_THREADS = 256;                               // a team of 8 warps works on its own group
+constexpr int S3_TEAMS = S3_THREADS / TEAM_THREADS;
 constexpr uint32_t SPAN_SUBS = 4;
 constexpr uint32_t SPAN_BITS = SPAN_SUBS * SUB_BITS;            // 1024
 constexpr uint32_t SPAN_WORDS = SPAN_BITS / 32;                 // 32
 constexpr uint32_t ROW_WORDS = SPAN_WORDS + 1;
-constexpr uint32_t GROUP_CHUNKS = S3_THREADS * SPAN_SUBS / DEC_THREADS;    // 8
-constexpr unsigned long long GROUP_BITS = (unsigned long long)S3_THREADS * SPAN_BITS;
+constexpr uint32_t GROUP_CHUNKS = TEAM_THREADS * SPAN_SUBS / DEC_THREADS;  // 2
+constexpr unsigned long long GROUP_BITS = (unsigned long long)TEAM_THREADS * SPAN_BITS;
 constexpr uint32_t SEG_BITS = 128;                              // checkpoint spacing
 constexpr uint32_t NSEG = SPAN_BITS / SEG_BITS;                 // 8
 constexpr size_t S3_SMEM = (4u << MICRO_K) + (size_t)S3_THREADS * ROW_WORDS * 4;
@@ -291,6 +293,18 @@ __device__ __forceinline__ uint32_t span_limit(unsigned long long X, unsigned lo
     return room >= SPAN_BITS ? SPAN_BITS : (uint32_t)room;
 }
 
+__device__ __forceinline__ void team_sync(uint32_t team)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TEAM_THREADS) : "memory");
+}
+__device__ __forceinline__ bool team_or(uint32_t team, bool pred)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"((uint32_t)pred), "r"(team + 1), "r"(TEAM_THREADS) : "memory");
+    return r != 0;
+}
+
 __global__ void __launch_bounds__(S3_THREADS, 1)
 dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
@@ -306,6 +320,7 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t team = tid / TEAM_THREADS, tt = tid % TEAM_THREADS;      // my team, my index in it
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);       // lengths only
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
@@ -314,32 +329,35 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     const uint32_t g = speculative ? 1u : tab->len_gcd;
     const uint32_t k2shift = 32u - tab->k2;
     const uint32_t *row = s_bits + tid * ROW_WORDS;
+    uint32_t *team_rows = s_bits + team * TEAM_THREADS * ROW_WORDS;
     uint32_t bad = 0;
+    __syncthreads();                                    // planes loaded
 
-    for (unsigned long long grp = g_first + blockIdx.x; grp < g_last; grp += gridDim.x) {
-        __syncthreads();                                // planes loaded / s_bits, s_wend, s_red reuse
-        // ---- stage the group's 128 KiB: 8 coalesced 128-bit loads per thread ----
+    for (unsigned long long grp = g_first + (unsigned long long)blockIdx.x * S3_TEAMS + team; grp < g_last;
+         grp += (unsigned long long)gridDim.x * S3_TEAMS) {
+        team_sync(team);                                // my team's rows, s_wend, s_red are free again
+        // ---- stage the group's 32 KiB: 8 coalesced 128-bit loads per thread ----
         const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
 #pragma unroll
         for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
-            const uint32_t v = tid + k * S3_THREADS;    // 16-byte vector of the group
+            const uint32_t v = tt + k * TEAM_THREADS;   // 16-byte vector of the group
             const unsigned long long b = gbyte0 + 16ull * v;
             uint4 x = make_uint4(0, 0, 0, 0);
             if (b < frame_bytes) x = ld_stream_v4(frame + b);          // the frame is 16-byte aligned
-            uint32_t *dst = s_bits + (v >> 3) * ROW_WORDS + 4 * (v & 7);
+            uint32_t *dst = team_rows + (v >> 3) * ROW_WORDS + 4 * (v & 7);
             dst[0] = bswap32(x.x); dst[1] = bswap32(x.y); dst[2] = bswap32(x.z); dst[3] = bswap32(x.w);
         }
         {   // the pad word of my row: the first word of the next span
-            const unsigned long long b = gbyte0 + (unsigned long long)(tid + 1) * (SPAN_BITS / 8);
+            const unsigned long long b = gbyte0 + (unsigned long long)(tt + 1) * (SPAN_BITS / 8);
             uint32_t x = 0;
             if (b < frame_bytes) x = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b)));
             s_bits[tid * ROW_WORDS + SPAN_WORDS] = x;
         }
-        __syncthreads();
+        team_sync(team);
 
-        const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tid * SPAN_BITS;
+        const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tt * SPAN_BITS;
         const uint32_t lim = span_limit(X, range_end_bit);     // code words starting at or after the range end are not ours
-        const bool fixed = (grp == 0 && tid == 0 && !speculative);  // holds the first payload bit: exact start
+        const bool fixed = (grp == 0 && tt == 0 && !speculative);   // holds the first payload bit: exact start
         uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
         uint32_t end = 0;
         Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
@@ -352,7 +370,7 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
         // shared memory, which usually moves only lane 0 of each warp.
         const bool movable = !fixed && lim != 0;
         uint32_t q0 = p;                                // lane 0's start: the guess, then the previous warp's overflow
-        for (uint32_t round = 0; round < S3_THREADS / 32 + 2; round++) {
+        for (uint32_t round = 0; round < TEAM_THREADS / 32 + 2; round++) {
             for (;;) {
                 uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
                 if (lane == 0) q = q0;
@@ -365,9 +383,9 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
                 }
             }
             if (lane == 31) s_wend[wid] = end;
-            __syncthreads();
-            q0 = wid ? s_wend[wid - 1] : p;
-            if (!__syncthreads_or(lane == 0 && movable && q0 != p)) break;
+            team_sync(team);
+            q0 = (tt >> 5) ? s_wend[wid - 1] : p;
+            if (!team_or(team, lane == 0 && movable && q0 != p)) break;
         }
 
         // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
@@ -382,7 +400,7 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
             total += cnt4[j];
             packed |= (unsigned long long)((pj & 63u) | (cnt4[j] << 6)) << (16 * j);
         }
-        const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tid * SPAN_SUBS;
+        const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tt * SPAN_SUBS;
         if (sub_index < nch * DEC_THREADS)              // info holds whole chunks: 4 records never straddle its end
             *reinterpret_cast<unsigned long long *>(L.info + sub_index) = packed;
         // chunk totals: a chunk is 128 consecutive threads (4 warps)
@@ -390,18 +408,18 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
         if (lane == 0) s_red[wid] = v;
-        __syncthreads();
+        team_sync(team);
         constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
-        const unsigned long long c = grp * GROUP_CHUNKS + tid / TPC;
+        const unsigned long long c = grp * GROUP_CHUNKS + tt / TPC;
         if (c < nch) {
-            if (tid % TPC == 0) {
+            if (tt % TPC == 0) {
                 uint32_t tot = 0;
 #pragma unroll
                 for (uint32_t i = 0; i < TPC / 32; i++) tot += s_red[wid + i];
                 L.chunkCnt[c] = tot;
                 L.chunkE2[c] = 0xFFFFFFFFu;
             }
-            if (tid % TPC == TPC - 1) L.chunkE[c] = end;
+            if (tt % TPC == TPC - 1) L.chunkE[c] = end;
         }
         // the thread whose span holds the end of the range reports the overflow past it
         if (lim && span_limit(X + SPAN_BITS, range_end_bit) == 0) work->result[1] = end;
@@ -679,10 +697,10 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
         attr = true;
     }
     const unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
-    // tail_only: the overflow past the range end, speculatively from a guessed start one or two groups
-    // (128 .. 256 KiB of self-synchronisation) before it
-    const unsigned long long g_first = tail_only ? (ngroups > 2 ? ngroups - 2 : 0) : 0;
-    unsigned long long grid = ngroups - g_first;
+    // tail_only: the overflow past the range end, speculatively from a guessed start up to eight groups
+    // (224 .. 256 KiB of self-synchronisation) before it
+    const unsigned long long g_first = tail_only ? (ngroups > 8 ? ngroups - 8 : 0) : 0;
+    unsigned long long grid = (ngroups - g_first + S3_TEAMS - 1) / S3_TEAMS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_sync3_kernel");
     dec_sync3_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
