@@ -354,6 +354,55 @@ def test_archive_extract_programs(oracle, romeo):
         assert subprocess.run([extract], cwd=td, capture_output=True).returncode == 1      # D:51-56
 
 
+def test_compress_unaligned_input_and_ragged_sizes(codec, oracle):
+    # the encoder works on 1 KiB units of a 16-byte aligned input; any 2-byte aligned input of any size must give
+    # the same bytes (scalar loads, ragged last unit, a last unit that owns no word of the stream)
+    data = synth.zipf_bytes((3 << 20) + 4096, 1.2, 21)
+    d = dev(data)
+    for off, n in ((0, 3 << 20), (2, (3 << 20) + 1), (6, (1 << 20) + 1022), (14, 1026), (16, 1024), (30, 2050), (0, 1023)):
+        want = oracle.compress(data[off:off + n])
+        got = codec.compress(d[off:off + n]).cpu().numpy()
+        assert np.array_equal(got, want), (off, n)
+        assert torch.equal(codec.decompress(dev(want)), d[off:off + n]), (off, n)
+
+
+def test_encode_units_larger_than_the_staging_window(codec, oracle):
+    # runs of the rarest symbols (codes of 30..44 bits): a 512-symbol unit holds ~20,000 bits, more than the
+    # encoder's 11,904-bit staging window -> the multi-pass general path; the decoder takes its slowest table path
+    h = fibonacci_hist(45)
+    syms = np.flatnonzero(h).astype(np.uint16)
+    ocb = oracle.codebook(h)
+    _, o_len, o_code = ocb.arrays()
+    rare = syms[np.argsort(-o_len[syms].astype(np.int64))][:8]
+    rng = np.random.default_rng(11)
+    data = np.concatenate([rng.choice(rare, 3000), rng.choice(syms, 5000), rng.choice(rare, 2047)]).astype(np.uint16)
+    bitstr = "".join(format(int(o_code[s]), "b").zfill(int(o_len[s])) for s in data)
+    cb = codec.build_codebook(dev(h.astype(np.int64)))
+    table = codec.decode_table_from_codebook(cb)
+    for start_bit in (0, 5):
+        want = np.packbits(np.frombuffer(("0" * start_bit + bitstr).encode(), np.uint8) - ord("0"))
+        out = torch.zeros(want.size + 64, dtype=torch.uint8, device="cuda")
+        codec.encode(dev(data.view(np.uint8)), cb, out, start_bit)
+        assert np.array_equal(out.cpu().numpy()[: want.size], want), start_bit
+        dec = torch.empty(data.size * 2, dtype=torch.uint8, device="cuda")
+        codec.decode(out, start_bit, data.size, table, dec)
+        codec.sync()
+        assert np.array_equal(dec.cpu().numpy().view(np.uint16), data)
+
+
+def test_round_trip_across_chunk_and_group_boundaries(codec, oracle):
+    # payload sizes around the decoder's 16 KiB chunks and 32 KiB groups, and around the 1 KiB spans in them
+    base = synth.mixed(1 << 20, seg_bytes=1 << 16)
+    img_full = oracle.compress(base)
+    for n in (40000, 40002, 41000, 65536, 65538, 81920, 131072, 131074, 163840, 262144, (1 << 20) - 2, 1 << 20):
+        data = base[:n]
+        want = oracle.compress(data)
+        got = codec.compress(dev(data))
+        assert np.array_equal(got.cpu().numpy(), want), n
+        assert torch.equal(codec.decompress(got), dev(data)), n
+    assert np.array_equal(codec.compress(dev(base)).cpu().numpy(), img_full)
+
+
 # ---------------------------------------------------------------- full-size properties (configs 4 and 5)
 def test_zipf1g_properties(codec, oracle):
     n = 1 << 30
