@@ -528,18 +528,19 @@ __global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigne
 constexpr uint32_t DSCAN_PER_BLOCK = 4096;
 
 __global__ void __launch_bounds__(1024)
-dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long *block_tot, const unsigned long long *gate)
+dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
+                 unsigned long long *block_tot, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     __shared__ unsigned long long s_w[33];
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr uint32_t PER = DSCAN_PER_BLOCK / 1024;
-    const unsigned long long i0 = (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + tid * PER;
+    const unsigned long long i0 = c0 + (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + tid * PER;
     uint32_t v[PER];
     unsigned long long sum = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < PER; j++) { v[j] = i0 + j < nch ? L.chunkCnt[i0 + j] : 0u; sum += v[j]; }
+    for (uint32_t j = 0; j < PER; j++) { v[j] = i0 + j < c1 ? L.chunkCnt[i0 + j] : 0u; sum += v[j]; }
     unsigned long long x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
@@ -555,7 +556,7 @@ dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long *bloc
     __syncthreads();
     unsigned long long run = x - sum + s_w[wid];
 #pragma unroll
-    for (uint32_t j = 0; j < PER; j++) { if (i0 + j < nch) L.chunkBase[i0 + j] = run; run += v[j]; }
+    for (uint32_t j = 0; j < PER; j++) { if (i0 + j < c1) L.chunkBase[i0 + j] = run; run += v[j]; }
     if (tid == 0) block_tot[blockIdx.x] = s_w[32];
 }
 
@@ -579,23 +580,28 @@ dec_scan2_kernel(DecWork *work, unsigned long long *block_tot, uint32_t nblocks,
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
         s_w[lane] = t - s;
-        if (lane == 31) work->result[2] = t;                // symbols in the whole range
+        if (lane == 31) s_w[32] = t;
     }
     __syncthreads();
-    unsigned long long run = x - sum + s_w[wid];
+    // work->result[2]: symbols of the chunks before this slice (0 for the first or only slice), then of all so far
+    const unsigned long long carry = work->result[2];
+    unsigned long long run = carry + x - sum + s_w[wid];
     for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = block_tot[i]; block_tot[i] = run; run += v; }
+    __syncthreads();
+    if (tid == 0) work->result[2] = carry + s_w[32];
 }
 
 __global__ void __launch_bounds__(1024)
-dec_scan3_kernel(DecWork *work, unsigned long long nch, const unsigned long long *block_tot, const unsigned long long *gate)
+dec_scan3_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
+                 const unsigned long long *block_tot, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     DecLayout L(work, nch);
     const unsigned long long add = block_tot[blockIdx.x];
     if (add == 0) return;
     for (uint32_t j = threadIdx.x; j < DSCAN_PER_BLOCK; j += 1024) {
-        const unsigned long long i = (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + j;
-        if (i < nch) L.chunkBase[i] += add;
+        const unsigned long long i = c0 + (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + j;
+        if (i < c1) L.chunkBase[i] += add;
     }
 }
 
@@ -691,13 +697,14 @@ __global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned lo
 int launch_table_planes(Ctx *c, DecodeTable *d_tab);             // decode2.cu
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 bool tail_only, const unsigned long long *gate);
+                 unsigned long long c0, unsigned long long c1, bool tail_only, const unsigned long long *gate);
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
-                  const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long n_symbols,
-                  uint16_t *out, const unsigned long long *gate);
+                  const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, const unsigned long long *gate);
 
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
-                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, const unsigned long long *gate);
+                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
+                unsigned long long c1, const unsigned long long *gate);
 
 static bool use_old_kernels()
 {   // development switch: HF_DECODE_OLD=1 runs decode.cu's first-generation kernels (A/B timing)
@@ -758,39 +765,52 @@ int launch_decode_fast(Ctx *c, const uint8_t *frame, long long hi_valid, long lo
 
 // the exact kernels; gate == nullptr runs them unconditionally, otherwise only when the single-pass
 // decoder raised one of DF_GATE_MASK (decided on the device: hf_decode stays asynchronous)
+// the scan of the chunk counts of [c0, c1); work->result[2] carries the symbols before c0 in and those before c1 out
+static int launch_scan(Ctx *c, DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
+                       const unsigned long long *gate)
+{
+    if (c1 <= c0) return HF_OK;
+    const uint32_t nblocks = (uint32_t)((c1 - c0 + DSCAN_PER_BLOCK - 1) / DSCAN_PER_BLOCK);
+    unsigned long long *block_tot = reinterpret_cast<unsigned long long *>(c->d_scan);
+    if (nblocks > SCAN_BLOCKS_MAX) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
+    HF_PROF(c, "dec_scan1_kernel"); dec_scan1_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot, gate);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dec_scan2_kernel"); dec_scan2_kernel<<<1, 1024, 0, c->stream>>>(work, block_tot, nblocks, gate);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dec_scan3_kernel"); dec_scan3_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot, gate);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+// The exact kernels over the chunks [c0, c1) of the frame: the whole stream in one go, or one slice of a pipelined
+// host-buffer decode (slices in order; c0 a multiple of 2).  gate == nullptr runs them unconditionally, otherwise
+// only when the single-pass decoder raised one of DF_GATE_MASK (decided on the device: hf_decode stays asynchronous).
 static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                                unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
-                               uint16_t *out16, DecWork *work, unsigned long long nch, const unsigned long long *gate)
+                               uint16_t *out16, DecWork *work, unsigned long long nch, unsigned long long c0,
+                               unsigned long long c1, const unsigned long long *gate)
 {
-    const bool old = use_old_kernels();
-    if (old) {
-        HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
-        HF_LAUNCH_CHECK(c);
-    } else {
-        int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, false, gate);
+    int rc;
+    if (!use_old_kernels()) {
+        rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false, gate);
         if (rc) return rc;
+        rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
+        if (rc) return rc;
+        rc = launch_scan(c, work, nch, c0, c1, gate);
+        if (rc) return rc;
+        return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16, gate);
     }
-    if (!old) {
-        int rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
-        if (rc) return rc;
-    } else if (nch > 1) {
+    // HF_DECODE_OLD=1: the first-generation kernels, whole stream only
+    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
+    HF_LAUNCH_CHECK(c);
+    if (nch > 1) {
         HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
         HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
         HF_LAUNCH_CHECK(c);
     }
-    {
-        const uint32_t nblocks = (uint32_t)((nch + DSCAN_PER_BLOCK - 1) / DSCAN_PER_BLOCK);
-        unsigned long long *block_tot = reinterpret_cast<unsigned long long *>(c->d_scan);
-        if (nblocks > SCAN_BLOCKS_MAX) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
-        HF_PROF(c, "dec_scan1_kernel"); dec_scan1_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, block_tot, gate);
-        HF_LAUNCH_CHECK(c);
-        HF_PROF(c, "dec_scan2_kernel"); dec_scan2_kernel<<<1, 1024, 0, c->stream>>>(work, block_tot, nblocks, gate);
-        HF_LAUNCH_CHECK(c);
-        HF_PROF(c, "dec_scan3_kernel"); dec_scan3_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, block_tot, gate);
-        HF_LAUNCH_CHECK(c);
-    }
-    if (!old) return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16, gate);
+    rc = launch_scan(c, work, nch, 0, nch, gate);
+    if (rc) return rc;
     const size_t wsmem = (SW_PADDED + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
     static bool wattr = false;
     if (!wattr) {
@@ -838,7 +858,7 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
         if (rc) return rc;
         gate = reinterpret_cast<const unsigned long long *>((uint8_t *)fast_work + 16) + 3;     // DfWork::result[3]
     }
-    return launch_decode_exact(c, frame, frame_bytes, F0, frame_bytes * 8, n_symbols, d_tab, out16, work, nch, gate);
+    return launch_decode_exact(c, frame, frame_bytes, F0, frame_bytes * 8, n_symbols, d_tab, out16, work, nch, 0, nch, gate);
 }
 
 // result[4] of a range call from the exact kernels' work area: -, overflow, symbols, flags
@@ -891,12 +911,12 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
             HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
             HF_LAUNCH_CHECK(c);
         } else {
-            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, true, nullptr);
+            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true, nullptr);
             if (rc) return rc;
         }
     } else {
         rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
-                                 work, nch, nullptr);
+                                 work, nch, 0, nch, nullptr);
         if (rc) return rc;
     }
     HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, tail_only ? ~0ull >> 8 : out_symbols, d_result);

@@ -434,7 +434,8 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
 __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                  unsigned long long n_symbols, uint16_t *__restrict__ out, const unsigned long long *gate)
+                  unsigned long long c0, unsigned long long c1, unsigned long long n_symbols,
+                  uint16_t *__restrict__ out, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     extern __shared__ __align__(16) uint32_t w3_smem[];
@@ -456,9 +457,9 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t bad = 0;
     constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
-    const unsigned long long nunits = nch * UPC;
+    const unsigned long long nunits = c1 * UPC;     // units of the chunks [c0, c1)
 
-    for (unsigned long long ug = (unsigned long long)blockIdx.x * W3_WARPS + wid; ug < nunits;
+    for (unsigned long long ug = c0 * UPC + (unsigned long long)blockIdx.x * W3_WARPS + wid; ug < nunits;
          ug += (unsigned long long)gridDim.x * W3_WARPS) {
         const unsigned long long c = ug / UPC;
         const uint32_t u = (uint32_t)(ug % UPC);
@@ -644,11 +645,12 @@ __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigne
 
 __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                                unsigned long long nch, const unsigned long long *gate)
+                                unsigned long long nch, unsigned long long c0, unsigned long long c1,
+                                const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
-    const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (c >= nch || tab->single_sym) return;
+    const unsigned long long c = c0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;    // c0 >= 1
+    if (c >= c1 || tab->single_sym) return;
     DecLayout L(work, nch);
     const uint32_t s = L.chunkE[c - 1];
     if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
@@ -660,13 +662,14 @@ __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long
 // streams that do not synchronise within a whole chunk: carry the true start forward serially
 __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                        unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
-                                       DecWork *work, unsigned long long nch, const unsigned long long *gate)
+                                       DecWork *work, unsigned long long nch, unsigned long long c0,
+                                       unsigned long long c1, const unsigned long long *gate)
 {
     if (gate && !(*gate & DF_GATE_MASK)) return;
     if (work->flags[0] == 0 || tab->single_sym) return;
     DecLayout L(work, nch);
     uint32_t bad = 0;
-    for (unsigned long long c = 1; c < nch; c++) {
+    for (unsigned long long c = c0; c < c1; c++) {          // c0 >= 1
         if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix2_kernel used
         const uint32_t s = L.chunkE2[c - 1];
         if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
@@ -675,31 +678,41 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
+// chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
-                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, const unsigned long long *gate)
+                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
+                unsigned long long c1, const unsigned long long *gate)
 {
-    if (nch <= 1) return HF_OK;
-    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
+    if (c0 == 0) c0 = 1;
+    if (c1 <= c0) return HF_OK;
+    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((c1 - c0 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
+    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
+// chunks [c0, c1), c0 a multiple of GROUP_CHUNKS; tail_only ignores the range
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 bool tail_only, const unsigned long long *gate)
+                 unsigned long long c0, unsigned long long c1, bool tail_only, const unsigned long long *gate)
 {
     static bool attr = false;
     if (!attr) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         attr = true;
     }
-    const unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
+    unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
     // tail_only: the overflow past the range end, speculatively from a guessed start up to eight groups
     // (224 .. 256 KiB of self-synchronisation) before it
-    const unsigned long long g_first = tail_only ? (ngroups > 8 ? ngroups - 8 : 0) : 0;
+    unsigned long long g_first = tail_only ? (ngroups > 8 ? ngroups - 8 : 0) : 0;
+    if (!tail_only) {
+        if (c0 % GROUP_CHUNKS) return set_err(c, HF_ERR_INTERNAL, "decode slice does not start at a group");
+        g_first = c0 / GROUP_CHUNKS;
+        ngroups = (c1 + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
+        if (ngroups <= g_first) return HF_OK;
+    }
     unsigned long long grid = (ngroups - g_first + S3_TEAMS - 1) / S3_TEAMS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_sync3_kernel");
@@ -710,18 +723,19 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
 }
 
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
-                  const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long n_symbols,
-                  uint16_t *out, const unsigned long long *gate)
+                  const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, const unsigned long long *gate)
 {
+    if (c1 <= c0) return HF_OK;
     static bool attr = false;
     if (!attr) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         attr = true;
     }
-    unsigned long long grid = (nch * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
+    unsigned long long grid = ((c1 - c0) * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out, gate);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, gate);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -12,7 +12,7 @@ mb = int(os.environ.get("BIG_MB", "256"))
 kind = os.environ.get("KIND", "zipf")
 n = mb << 20
 codec = Codec(0)
-d = synth.zipf1g(n, device="cuda") if kind == "zipf" else synth.mixed(n, seg_bytes=n // 6, device="cuda")
+d = synth.zipf1g(n, device="cuda") if kind == "zipf" else synth.mixed(n, seg_bytes=n // 16, device="cuda")
 out = torch.empty(codec.compress_bound(n), dtype=torch.uint8, device="cuda")
 back = torch.empty(n, dtype=torch.uint8, device="cuda")
 for it in range(2):
