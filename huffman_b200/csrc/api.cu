@@ -107,6 +107,8 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     c->own_stream = false;
     c->decode_exact_only = true;                        // see hf_set_decode_mode
     bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&c->h_pipe, PIPE_SLOTS * 8) == cudaSuccess;
     for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scratch, 4096) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_cb, codebook_alloc_bytes()) == cudaSuccess;
@@ -126,6 +128,8 @@ int hf_ctx_destroy(hf_ctx *ctx)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+    if (c->h_pipe) cudaFreeHost(c->h_pipe);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->ws) cudaFree(c->ws);
@@ -531,6 +535,13 @@ int hf_decompressed_size_host(const uint8_t *h_file, uint64_t file_bytes, uint64
     return HF_OK;
 }
 
+// Host buffers in, host buffers out.  Large images are pipelined: the header is parsed from the first MiB while the
+// payload is still crossing PCIe in slices; each slice is decoded as it lands and its symbols leave on a third stream,
+// so the H2D copy of the image, the kernels and the D2H copy of the output overlap (the reference reads the file with
+// fread per byte and decodes on the host, D:259-291).
+static const uint64_t PIPE_MIN_BYTES = 64ull << 20;
+static const uint64_t PIPE_SLICE_CHUNKS = 16384;        // 256 MiB of payload per slice
+
 int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, uint8_t *h_out, uint64_t capacity,
                        uint64_t *h_out_bytes)
 {
@@ -538,12 +549,15 @@ int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, 
     Ctx *c = CTX(ctx);
     if (!h_file) return set_err(c, HF_ERR_ARG, "hf_decompress_host: null pointer");
     if (file_bytes < 11) return set_err(c, HF_ERR_FORMAT, "hf_decompress_host: image too short");
-    int rc = ensure_buf(c, &c->d_out, &c->d_out_bytes, file_bytes + 32);
+    int rc = ensure_buf(c, &c->d_out, &c->d_out_bytes, file_bytes + 128);
     if (rc) return rc;
     uint8_t *d_file = reinterpret_cast<uint8_t *>(c->d_out);
-    HF_CUDA(c, cudaMemcpyAsync(d_file, h_file, file_bytes, cudaMemcpyHostToDevice, c->stream));
+    // the header (at most ~720 KiB) first
+    const bool piped = file_bytes >= PIPE_MIN_BYTES;
+    const uint64_t first = piped ? (1ull << 20) : file_bytes;
+    HF_CUDA(c, cudaMemcpyAsync(d_file, h_file, first, cudaMemcpyHostToDevice, c->stream));
     hf_header_info_t info;
-    rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);
+    rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);     // synchronises
     if (rc) return rc;
     if (h_out_bytes) *h_out_bytes = info.original_bytes;
     if (info.original_bytes > capacity)
@@ -554,14 +568,88 @@ int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, 
     if (rc) return rc;
     uint8_t *d_out = reinterpret_cast<uint8_t *>(c->d_in);
     const uint64_t nsym = info.original_bytes / 2;
-    if (nsym) {
-        rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, reinterpret_cast<DecodeTable *>(c->d_tab), d_out);
-        if (rc) return rc;
-        HF_CUDA(c, cudaMemcpyAsync(h_out, d_out, nsym * 2, cudaMemcpyDeviceToHost, c->stream));
-        rc = check_decode_flags(c);
-        if (rc) return rc;
+    DecodeTable *tab = reinterpret_cast<DecodeTable *>(c->d_tab);
+
+    if (!piped || nsym == 0 || info.n_unique <= 1) {
+        if (first < file_bytes)
+            HF_CUDA(c, cudaMemcpyAsync(d_file + first, h_file + first, file_bytes - first, cudaMemcpyHostToDevice, c->stream));
+        if (nsym) {
+            rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, tab, d_out);
+            if (rc) return rc;
+            HF_CUDA(c, cudaMemcpyAsync(h_out, d_out, nsym * 2, cudaMemcpyDeviceToHost, c->stream));
+            rc = check_decode_flags(c);
+            if (rc) return rc;
+        } else {
+            HF_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        if (info.is_odd) h_out[info.original_bytes - 1] = (uint8_t)info.last_byte;      // D:286-289
+        return HF_OK;
     }
-    if (info.is_odd) h_out[info.original_bytes - 1] = (uint8_t)info.last_byte;      // D:286-289
+
+    DecodeJob job;
+    rc = decode_begin(c, d_file, file_bytes, info.payload_start_bit, nsym, tab, d_out, &job);
+    if (rc) return rc;
+    const uint64_t frame_off = (uint64_t)(job.frame - d_file);          // file byte of frame byte 0
+    const uint64_t slice_bytes = PIPE_SLICE_CHUNKS * 16384ull;
+    const uint64_t nsl = (job.nch + PIPE_SLICE_CHUNKS - 1) / PIPE_SLICE_CHUNKS;
+    if (nsl > PIPE_SLOTS) return set_err(c, HF_ERR_ARG, "hf_decompress_host: image too large");
+    cudaEvent_t *ev = (cudaEvent_t *)calloc(2 * nsl, sizeof(cudaEvent_t));
+    if (!ev) return set_err(c, HF_ERR_ARG, "hf_decompress_host: out of memory");
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->d2h_stream);
+        for (uint64_t i = 0; i < 2 * nsl; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+        free(ev);
+        return code;
+    };
+#define PIPE_CUDA(call)                                                                                     \
+    do {                                                                                                    \
+        cudaError_t _e = (call);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return cleanup(set_err(c, HF_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e))); \
+    } while (0)
+    for (uint64_t i = 0; i < 2 * nsl; i++) PIPE_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    // the payload crosses PCIe slice by slice (each with 64 bytes of the next: the kernels look a few bytes ahead)
+    for (uint64_t k = 0; k < nsl; k++) {
+        uint64_t lo = frame_off + k * slice_bytes, hi = frame_off + (k + 1) * slice_bytes + 64;
+        if (lo < first) lo = first;
+        if (hi > file_bytes) hi = file_bytes;
+        if (hi > lo) PIPE_CUDA(cudaMemcpyAsync(d_file + lo, h_file + lo, hi - lo, cudaMemcpyHostToDevice, c->copy_stream));
+        PIPE_CUDA(cudaEventRecord(ev[2 * k], c->copy_stream));
+    }
+    uint64_t sent = 0;                                  // symbols already on their way to the host
+    auto drain = [&](uint64_t k) -> int {               // the symbols slice k completed leave on the third stream
+        cudaError_t e = cudaEventSynchronize(ev[2 * k + 1]);
+        if (e != cudaSuccess) return set_err(c, HF_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+        uint64_t tot = c->h_pipe[k] < nsym ? c->h_pipe[k] : nsym;
+        if (k + 1 == nsl) tot = nsym;
+        if (tot > sent) {
+            e = cudaStreamWaitEvent(c->d2h_stream, ev[2 * k + 1], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(h_out + 2 * sent, d_out + 2 * sent, 2 * (tot - sent), cudaMemcpyDeviceToHost, c->d2h_stream);
+            if (e != cudaSuccess) return set_err(c, HF_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+            sent = tot;
+        }
+        return HF_OK;
+    };
+    for (uint64_t k = 0; k < nsl; k++) {
+        PIPE_CUDA(cudaStreamWaitEvent(c->stream, ev[2 * k], 0));
+        const uint64_t c0 = k * PIPE_SLICE_CHUNKS, c1 = (k + 1) * PIPE_SLICE_CHUNKS < job.nch ? (k + 1) * PIPE_SLICE_CHUNKS : job.nch;
+        rc = decode_slice(c, job, c0, c1);
+        if (rc) return cleanup(rc);
+        PIPE_CUDA(cudaMemcpyAsync(&c->h_pipe[k], job.total, 8, cudaMemcpyDeviceToHost, c->stream));
+        PIPE_CUDA(cudaEventRecord(ev[2 * k + 1], c->stream));
+        if (k) { rc = drain(k - 1); if (rc) return cleanup(rc); }
+    }
+    rc = drain(nsl - 1);
+    if (rc) return cleanup(rc);
+#undef PIPE_CUDA
+    rc = cleanup(HF_OK);
+    if (rc) return rc;
+    rc = check_decode_flags(c);
+    if (rc) return rc;
+    if (info.is_odd) h_out[info.original_bytes - 1] = (uint8_t)info.last_byte;          // D:286-289
     return HF_OK;
 }
 

@@ -114,6 +114,8 @@ struct Ctx {
     void *h_scratch;
     // second stream + events for the host-buffer pipelines
     cudaStream_t copy_stream;
+    cudaStream_t d2h_stream;        // results leave on their own stream (hf_decompress_host)
+    unsigned long long *h_pipe;     // pinned: running symbol counts of the slices (PIPE_SLOTS)
     cudaEvent_t ev[8];
     // cached device buffers for the host-facing calls
     void *d_in; size_t d_in_bytes;
@@ -131,6 +133,7 @@ struct Ctx {
     const char **prof_name;         // PROF_CAP static strings
 };
 constexpr uint32_t PROF_CAP = 8192;
+constexpr uint32_t PIPE_SLOTS = 4096;
 constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload
 void prof_begin(Ctx *c, const char *name);
 void prof_end(Ctx *c);
@@ -173,6 +176,18 @@ int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, Deco
 int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab);
 int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
                   uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out);
+// a decode in slices (decode.cu; hf_decompress_host pipelines host copies around them)
+struct DecodeJob {
+    const uint8_t *frame;               // 16-byte aligned base the chunks are counted from
+    unsigned long long frame_bytes, F0, nch, n_symbols;
+    const DecodeTable *tab;
+    uint16_t *out16;
+    void *work, *fast_work;
+    unsigned long long *total;          // device: symbols decoded by the slices so far
+};
+int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
+                 const DecodeTable *d_tab, uint8_t *d_out, DecodeJob *job);
+int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned long long c1);
 int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, uint64_t first_bit,
                         bool tail_only, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
                         unsigned long long *d_result);

@@ -822,43 +822,64 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
     return HF_OK;
 }
 
-int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
-                  uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out)
+// A decode of one stream, all at once (launch_decode) or in slices of chunks as its bytes arrive from the host
+// (hf_decompress_host): decode_begin lays out the frame and the work area, decode_slice runs the exact kernels on
+// the chunks [c0, c1) — slices in ascending order, c0 a multiple of 2.  job.total is the device address of the
+// running symbol count (symbols decoded by the slices so far).
+int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
+                 const DecodeTable *d_tab, uint8_t *d_out, DecodeJob *job)
 {
-    if (n_symbols == 0) return HF_OK;
     if ((uintptr_t)d_out & 1) return set_err(c, HF_ERR_ARG, "hf_decode: output must be 2-byte aligned");
     if ((start_bit >> 3) > stream_bytes) return set_err(c, HF_ERR_ARG, "hf_decode: start bit past the stream");
     d_stream += start_bit >> 3;
     stream_bytes -= start_bit >> 3;
     start_bit &= 7;
-    const uint8_t *frame = reinterpret_cast<const uint8_t *>((uintptr_t)d_stream & ~(uintptr_t)15);
+    job->frame = reinterpret_cast<const uint8_t *>((uintptr_t)d_stream & ~(uintptr_t)15);
     const unsigned long long lead = (uintptr_t)d_stream & 15;
-    const unsigned long long frame_bytes = lead + stream_bytes;
-    const unsigned long long F0 = lead * 8 + start_bit;
-    unsigned long long nch = (frame_bytes * 8 + CHUNK_BITS - 1) / CHUNK_BITS;
-    if (nch == 0) nch = 1;                              // zero-length codes: nothing to read
-    if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
-    const unsigned long long nch_fast = df_chunks(frame_bytes * 8);
-
+    job->frame_bytes = lead + stream_bytes;
+    job->F0 = lead * 8 + start_bit;
+    job->nch = (job->frame_bytes * 8 + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (job->nch == 0) job->nch = 1;                    // zero-length codes: nothing to read
+    if (job->nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
+    job->n_symbols = n_symbols;
+    job->tab = d_tab;
+    job->out16 = reinterpret_cast<uint16_t *>(d_out);
+    const unsigned long long nch_fast = df_chunks(job->frame_bytes * 8);
     const size_t off = 8u << 20;                        // behind the table-source / codebook workspace
-    const size_t exact_bytes = (DecLayout::bytes(nch) + 255) & ~(size_t)255;
+    const size_t exact_bytes = (DecLayout::bytes(job->nch) + 255) & ~(size_t)255;
     int rc = ensure_ws(c, off + exact_bytes + df_work_bytes(nch_fast));
     if (rc) return rc;
-    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
-    void *fast_work = (uint8_t *)c->ws + off + exact_bytes;
-    HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
-
-    uint16_t *out16 = reinterpret_cast<uint16_t *>(d_out);
-    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, out16);
+    job->work = (uint8_t *)c->ws + off;
+    job->fast_work = (uint8_t *)c->ws + off + exact_bytes;
+    job->total = reinterpret_cast<unsigned long long *>(job->work) + 2;     // DecWork::result[2]
+    HF_CUDA(c, cudaMemsetAsync(job->work, 0, sizeof(DecWork), c->stream));
+    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, job->out16);
     HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned long long c1)
+{
+    return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, job.n_symbols, job.tab, job.out16,
+                               reinterpret_cast<DecWork *>(job.work), job.nch, c0, c1, nullptr);
+}
+
+int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
+                  uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out)
+{
+    if (n_symbols == 0) return HF_OK;
+    DecodeJob job;
+    int rc = decode_begin(c, d_stream, stream_bytes, start_bit, n_symbols, d_tab, d_out, &job);
+    if (rc) return rc;
     const unsigned long long *gate = nullptr;
     if (!c->decode_exact_only) {
-        rc = launch_decode_fast(c, frame, (long long)frame_bytes, (long long)(frame_bytes * 8), (uint32_t)F0,
-                                n_symbols, d_tab, out16, fast_work, nch_fast, false);
+        rc = launch_decode_fast(c, job.frame, (long long)job.frame_bytes, (long long)(job.frame_bytes * 8), (uint32_t)job.F0,
+                                n_symbols, d_tab, job.out16, job.fast_work, df_chunks(job.frame_bytes * 8), false);
         if (rc) return rc;
-        gate = reinterpret_cast<const unsigned long long *>((uint8_t *)fast_work + 16) + 3;     // DfWork::result[3]
+        gate = reinterpret_cast<const unsigned long long *>((uint8_t *)job.fast_work + 16) + 3;     // DfWork::result[3]
     }
-    return launch_decode_exact(c, frame, frame_bytes, F0, frame_bytes * 8, n_symbols, d_tab, out16, work, nch, 0, nch, gate);
+    return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, n_symbols, d_tab, job.out16,
+                               reinterpret_cast<DecWork *>(job.work), job.nch, 0, job.nch, gate);
 }
 
 // result[4] of a range call from the exact kernels' work area: -, overflow, symbols, flags

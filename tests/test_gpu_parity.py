@@ -335,6 +335,21 @@ def test_host_calls_match_device_calls(codec, oracle):
     assert np.array_equal(image2.numpy(), want)
 
 
+def test_host_decompress_pipelined_in_slices(codec):
+    # images of 64 MiB and more are decoded in 256 MiB slices while the payload is still arriving from the host and
+    # the output is already leaving: three slices here, odd byte count, device path as the reference
+    n = (900 << 20) + 1
+    d = synth.mixed(n, seg_bytes=1 << 26, device="cuda")
+    image = codec.compress(d)
+    assert image.numel() > (512 << 20)
+    h_img = image.cpu().pin_memory()
+    back = codec.decompress_host(h_img)
+    assert back.numel() == n and torch.equal(back.cuda(), d)
+    # a pageable source and destination take the same path
+    back2 = codec.decompress_host(image.cpu(), torch.empty(n, dtype=torch.uint8))
+    assert torch.equal(back2.cuda(), d)
+
+
 def test_archive_extract_programs(oracle, romeo):
     """bin/archive and bin/extract keep the reference's command line and file names (Makefile:17-29)"""
     archive, extract = os.path.join(ROOT, "bin", "archive"), os.path.join(ROOT, "bin", "extract")
