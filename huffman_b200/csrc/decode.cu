@@ -934,6 +934,13 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
         } else {
             rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true, nullptr);
             if (rc) return rc;
+            // the (up to) 8 groups of the tail converge one by one on guessed starts; the repair carries the chain
+            // from the first of them (the lead-in, 224 KiB or more when the range is that long) to the range end
+            const unsigned long long ngroups = (nch + 1) / 2, g_first = ngroups > 8 ? ngroups - 8 : 0;
+#ifndef HF_NO_TAIL_FIX
+            rc = launch_fix2(c, frame, frame_bytes, end_bit, d_tab, work, nch, g_first * 2 + 1, nch, nullptr);
+            if (rc) return rc;
+#endif
         }
     } else {
         rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),

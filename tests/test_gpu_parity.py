@@ -293,6 +293,24 @@ def test_range_decode_matches_whole_decode(codec, oracle, romeo, exact_mode):
             assert np.array_equal(got, data[: data.size & ~1]), (data.size, world, cuts)
 
 
+def test_range_overflow_speculation_near_group_boundaries(codec, oracle):
+    # The hand-over bit of a range is speculated from its tail.  Flat data under a mixed codebook (17/18-bit codes)
+    # re-synchronises only after ~2,000 bits, and a range that ends a few bytes after one of the decoder's 32 KiB
+    # groups has almost no bits of its own group behind it: the chain must come from the groups before.
+    data = synth.mixed(12 << 20, seg_bytes=1 << 20)
+    image = oracle.compress(data)
+    hdr = (int(codec.parse_header(dev(image))[1].payload_start_bit) + 7) // 8
+    assert hdr < (1 << 20)
+    cuts, pos = [], 3 << 20                                         # inside the uniform segment and after it
+    for groups, extra in ((20, 8), (33, 40), (17, 200), (64, 2), (9, 32767)):
+        pos += groups * 32768 + extra
+        cuts.append(pos)
+    assert cuts[-1] < image.size
+    cuts = [3 << 20] + cuts
+    got = _decode_by_ranges(codec, image, cuts, True)               # asserts speculation == truth for every range
+    assert np.array_equal(got, data)
+
+
 def test_sharded_codec_single_rank(codec, oracle, romeo):
     """ShardedCodec with one rank: same stages, no collectives; byte-identical slices and round trip"""
     from huffman_b200.sharded import ShardedCodec
