@@ -36,6 +36,9 @@ constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code 
 #define W3_WARPS 24                                             // warps of the write kernel's CTA
 #endif
 constexpr int W3_THREADS = W3_WARPS * 32;
+#ifndef W3_PHASE
+#define W3_PHASE 2                                              // words per walk phase of the write kernel (1, 2, 4)
+#endif
 // output staging window of one warp (symbols, multiple of 8): what is left of the SM's 227 KiB beside the planes
 constexpr uint32_t W3_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - 64u) / W3_WARPS) / 2 - 8) & ~7u;
 constexpr size_t W3_SMEM = (4u << MICRO_K) + NSYM * 2 + (size_t)W3_WARPS * (W3_WIN + 8) * 2;
@@ -503,11 +506,17 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             if (o < o_end) {
                 uint16_t *sp = sout + (o - w0 + mis);
                 uint16_t *const sp_end = sout + (o_end - w0 + mis);
+                // phases of W3_PHASE words: the window's two words are picked by selects inside a phase; longer
+                // phases keep more lanes busy (a lane leaves a phase when its position passes the phase's end)
 #pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    const uint32_t lw = 32u * (w + 1);
+                for (int w = 0; w < 8; w += W3_PHASE) {
+                    const uint32_t lw = 32u * (w + W3_PHASE);
                     while (pos < lw && sp < sp_end) {
-                        const uint32_t win = __funnelshift_l(r[w + 1], r[w], pos);
+                        uint32_t hi = r[w], lo = r[w + 1];
+#pragma unroll
+                        for (int k = 1; k < W3_PHASE; k++)
+                            if (pos >= 32u * (w + k)) { hi = r[w + k]; lo = r[w + k + 1]; }
+                        const uint32_t win = __funnelshift_l(lo, hi, pos);
                         const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
                         uint32_t len, sym;
                         if (e14 & 1u) {
