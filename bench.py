@@ -205,12 +205,8 @@ KERNEL_BYTES = {
     "hist_smem_kernel": lambda n, c: n,
     "enc_bits_kernel": lambda n, c: n,
     "encode2_kernel": lambda n, c: n + c,
-    "enc_count_kernel": lambda n, c: n,         # HF_ENCODE_OLD=1: the first-generation kernels
-    "encode_kernel": lambda n, c: n + c,
     "dec_sync3_kernel": lambda n, c: c,
     "dec_write3_kernel": lambda n, c: c + n,
-    "dec_sync_kernel": lambda n, c: c,          # HF_DECODE_OLD=1: the first-generation kernels
-    "dec_write_kernel": lambda n, c: c + n,
 }
 
 

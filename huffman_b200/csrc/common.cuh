@@ -124,7 +124,7 @@ struct Ctx {
     void *d_tab;
     void *d_hist;
     void *d_scan;                   // block totals of the decoder's chunk scan (SCAN_BLOCKS_MAX u64)
-    bool decode_exact_only;         // hf_set_decode_mode(1): skip the single-pass decoder (tests)
+    bool decode_exact_only;         // hf_set_decode_mode: kept for ABI compatibility, the decoder has one (exact) mode
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
     bool prof_open;                 // a begin event is pending
@@ -182,7 +182,7 @@ struct DecodeJob {
     unsigned long long frame_bytes, F0, nch, n_symbols;
     const DecodeTable *tab;
     uint16_t *out16;
-    void *work, *fast_work;
+    void *work;
     unsigned long long *total;          // device: symbols decoded by the slices so far
 };
 int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,

@@ -11,26 +11,18 @@
 //   first mismatch confirms up to 32 entries per step (the table is sorted by count, so
 //   lengths come in long runs).  Any header parses correctly, sorted ones ~32x faster.
 //
-// Tables (dt_*): 12-bit primary table in shared memory, per-prefix secondary tables (up to
-//   +12 bits) in global memory (L1/L2 resident), a linear list for still longer codes.
+// Tables (dt_*): a general two-level table for any code length up to 64 bits (12-bit primary, per-prefix
+//   secondary tables of up to +12 bits, a linear list for still longer codes); decode2.cu derives the
+//   shared-memory planes of the hot kernels from it.
 //
-// Payload: chunks of 512 subsequences x 256 bits.
-//   A dec_sync_kernel   — every thread decodes its subsequence from the first position a code
-//       word can start at (exact when all code lengths share a gcd > 1, e.g. fixed-length
-//       codes), remembering the boundaries it met in its first 64 bits.  The true start is
-//       the predecessor's overflow; a thread re-synchronises by decoding from there only
-//       until it lands on a remembered boundary (a few code words).  Iterates to a fixed
-//       point inside the CTA.  Emits (start, count) per subsequence: 2 bytes per 32.
-//   B dec_fix_kernel    — one thread per chunk repairs the first subsequences from the true
-//       chunk start (the previous chunk's overflow); dec_fix_serial_kernel handles streams
-//       that fail to synchronise inside a whole chunk (correct, slow, practically never).
-//   S dec_scan_kernel   — exclusive scan of the chunk symbol counts.
-//   C dec_write_kernel  — decodes again from the known starts into a shared staging window
-//       and writes the symbols with aligned 128-bit stores.
+// Payload: chunks of 512 subsequences x 256 bits; the stages below run on a range of chunks (the whole stream,
+// or one slice of a pipelined host-buffer decode):
+//   dec_sync3_kernel (decode2.cu)   code word boundaries and counts per subsequence, exact
+//   dec_fix2_kernel  (decode2.cu)   repair of the first spans of a group from the previous group's overflow
+//   dec_scan1/2/3_kernel            exclusive scan of the chunk symbol counts
+//   dec_write3_kernel (decode2.cu)  symbols out
 //
-// Algorithmic bytes: C read + N written (the payload is read twice: traffic ~ 2C + N).
-#include <stdlib.h>
-
+// Algorithmic bytes: C read + N written (the payload is read twice: traffic ~ 2C + N + C/16).
 #include "common.cuh"
 #include "decode_common.cuh"
 
@@ -298,240 +290,14 @@ __global__ void dec_entries_kernel(const uint8_t *__restrict__ file, unsigned lo
     src->code[k] = code;
 }
 
-// -----------------------------------------------------------------------------------
-// chunk staging: frame words [c * CHUNK_WORDS, + CHUNK_WORDS + pad) as big-endian words
-__device__ __forceinline__ void stage_chunk(uint32_t *sw, const uint8_t *frame, unsigned long long frame_bytes,
-                                            unsigned long long chunk)
-{
-    const unsigned long long v0 = chunk * (CHUNK_WORDS / 4);
-    for (uint32_t i = threadIdx.x; i < (CHUNK_WORDS + CHUNK_PAD_WORDS) / 4; i += DEC_THREADS) {
-        unsigned long long byte = (v0 + i) * 16ull;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (byte < frame_bytes) v = ld_stream_v4(frame + byte);      // same 16-byte block as a valid byte
-        uint32_t *dst = sw + smem_word_index(4 * i);        // the four words share one pad group
-        dst[0] = bswap32(v.x); dst[1] = bswap32(v.y); dst[2] = bswap32(v.z); dst[3] = bswap32(v.w);
-    }
-}
-
-// full decode of one subsequence from offset p: overflow, count and the boundary mask of the first 64 bits
-template <typename F>
-__device__ __forceinline__ void sub_decode_count(const TabView &T, F f, uint32_t sub_bit0, uint32_t p, uint32_t lim,
-                                                 uint32_t &end, uint32_t &cnt_hi, unsigned long long &mask,
-                                                 uint32_t &bad)
-{
-    mask = 0; cnt_hi = 0;
-    if (p >= lim) { end = p - lim; return; }
-    BitReader<F> r{f};
-    r.init(sub_bit0 + p);
-    uint32_t pos = p;
-    while (pos < min(64u, lim)) {
-        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
-        mask |= 1ull << pos;
-        pos += len;
-        r.skip(len);
-    }
-    while (pos < lim) {
-        uint32_t len = decode_one(T, r, sub_bit0 + pos, bad) & 0x7Fu;
-        cnt_hi++;
-        pos += len;
-        r.skip(len);
-    }
-    end = pos - lim;
-}
-
-// Walks the code words of the subsequence at staged bit `sub0` from offset `from` up to `lim`, recording
-// every boundary in a 256-bit mask.  HIT: stop at the first position the OLD walk (mask on entry) also
-// visited and splice the old walk's remainder behind the new prefix — a re-synchronisation costs only
-// the few code words it takes to meet the old walk, wherever in the subsequence that happens.
-template <bool HIT>
-__device__ __forceinline__ bool walk_sub(const TabView &T, const uint32_t *sw, uint32_t sub0, uint32_t from, uint32_t lim,
-                                         unsigned long long (&mask)[4], uint32_t &cnt, uint32_t &end, uint32_t &bad)
-{
-    unsigned long long nm[4] = {0, 0, 0, 0};
-    uint32_t pos = from, k = 0;
-    bool hit = false;
-#pragma unroll
-    for (uint32_t s = 0; s < 4; s++) {
-        const uint32_t seg_end = min(lim, (s + 1) * 64);
-        const unsigned long long om = mask[s];
-        unsigned long long m = 0;
-        while (!hit && pos < seg_end) {
-            if (HIT && ((om >> (pos & 63)) & 1ull)) { hit = true; break; }
-            const uint32_t len = decode_at(T, sw, sub0 + pos, bad) & 0x7Fu;
-            m |= 1ull << (pos & 63);
-            k++;
-            pos += len;
-        }
-        nm[s] = m;
-    }
-    if (HIT && hit) {
-        const uint32_t hs = pos >> 6;
-        const unsigned long long keep = ~0ull << (pos & 63);        // old boundaries at or after the meeting point
-        uint32_t c = k;
-#pragma unroll
-        for (uint32_t s = 0; s < 4; s++) {
-            const unsigned long long old = s < hs ? 0ull : (s == hs ? (mask[s] & keep) : mask[s]);
-            c += __popcll(old);
-            mask[s] = nm[s] | old;
-        }
-        cnt = c;                                                     // `end` is the old walk's
-    } else {
-#pragma unroll
-        for (uint32_t s = 0; s < 4; s++) mask[s] = nm[s];
-        cnt = k;
-        end = pos - lim;
-    }
-    return hit;
-}
-
-__global__ void __launch_bounds__(DEC_THREADS)
-dec_sync_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
-                unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                unsigned long long nch, unsigned long long c0, uint32_t speculative, const unsigned long long *gate)
-{
-    if (gate && !(*gate & DF_GATE_MASK)) return;        // the single-pass decoder succeeded
-    __shared__ __align__(16) uint32_t sw[SW_PADDED];
-    __shared__ uint32_t st1[1u << K1];
-    __shared__ uint32_t s_end[DEC_THREADS];
-    if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
-    DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x;
-    const unsigned long long c = c0 + blockIdx.x;
-    for (uint32_t i = tid; i < (1u << K1); i += DEC_THREADS) st1[i] = tab->t1[i];
-    stage_chunk(sw, frame, frame_bytes, c);
-    __syncthreads();
-
-    TabView T{st1, tab->t2, tab->longs, tab->n_long};
-    const uint32_t g = speculative ? 1u : tab->len_gcd;
-    const uint32_t sub_bit0 = tid * SUB_BITS;
-    const unsigned long long X = c * CHUNK_BITS + sub_bit0;
-    const uint32_t lim = sub_limit(c, tid, range_end_bit);      // code words starting at or after the range end are not ours
-    const bool fixed = (c == 0 && tid == 0 && !speculative);    // holds the first payload bit: exact start
-    uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
-    uint32_t end = 0, cnt = 0, bad = 0;
-    unsigned long long mask[4] = {0, 0, 0, 0};
-    if (lim) {
-        if (p < lim) walk_sub<false>(T, sw, sub_bit0, p, lim, mask, cnt, end, bad);
-        else end = p - lim;
-    }
-
-    for (uint32_t it = 0; it < DEC_THREADS + 1; it++) {
-        s_end[tid] = end;
-        __syncthreads();
-        int changed = 0;
-        if (tid > 0 && !fixed && lim) {
-            const uint32_t q = s_end[tid - 1];
-            if (q != p) {
-                // re-synchronise: decode from q until a boundary the recorded walk also visited
-                const uint32_t old_end = end;
-                if (q < lim) walk_sub<true>(T, sw, sub_bit0, q, lim, mask, cnt, end, bad);
-                else { cnt = 0; end = q - lim; mask[0] = mask[1] = mask[2] = mask[3] = 0; }
-                changed = end != old_end;
-                p = q;
-            }
-        }
-        if (!__syncthreads_or(changed)) break;
-    }
-    L.info[c * DEC_THREADS + tid] = (uint16_t)((p & 63u) | (cnt << 6));
-    // chunk totals
-    uint32_t v = cnt;
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    __syncthreads();
-    if ((tid & 31) == 0) s_end[tid >> 5] = v;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t tot = 0;
-        for (int i = 0; i < DEC_THREADS / 32; i++) tot += s_end[i];
-        L.chunkCnt[c] = tot;
-        L.chunkE2[c] = 0xFFFFFFFFu;
-    }
-    if (tid == DEC_THREADS - 1) L.chunkE[c] = end;
-    // the thread whose subsequence holds the end of the range reports the overflow past it
-    if (lim && sub_limit(c, tid + 1, range_end_bit) == 0) work->result[1] = end;
-    if (bad) atomicExch(&work->flags[1], 1ull);
-}
-
-// repairs chunk c from the true start `s` (frame offset inside the chunk's subsequence 0).
-// Returns true when the walk re-joined the recorded chain before the chunk ended.
-__device__ bool fix_chunk(const TabView &T, const uint8_t *frame, unsigned long long frame_bytes,
-                          unsigned long long range_end_bit, DecWork *work, DecLayout &L, unsigned long long c, uint32_t s,
-                          uint32_t &bad)
-{
-    uint16_t *info = L.info + c * DEC_THREADS;
-    GlobalFetch f{frame, frame_bytes, c * CHUNK_WORDS};
-    uint32_t q = s;
-    long long delta = 0;
-    for (uint32_t t = 0; t < DEC_THREADS; t++) {
-        const uint32_t lim = sub_limit(c, t, range_end_bit);
-        if (lim == 0) break;
-        uint32_t end, cnt_hi;
-        unsigned long long mask;
-        sub_decode_count(T, f, t * SUB_BITS, q, lim, end, cnt_hi, mask, bad);
-        uint32_t cnt = __popcll(mask) + cnt_hi;
-        uint32_t old = info[t];
-        delta += (long long)cnt - (long long)(old >> 6);
-        info[t] = (uint16_t)((q & 63u) | (cnt << 6));
-        if (sub_limit(c, t + 1, range_end_bit) == 0) {          // the range ends in this subsequence
-            work->result[1] = end;
-            break;
-        }
-        if (t + 1 == DEC_THREADS) {
-            L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
-            uint32_t curE = L.chunkE2[c] != 0xFFFFFFFFu ? L.chunkE2[c] : L.chunkE[c];
-            if (end != curE) { L.chunkE2[c] = end; return false; }
-            return true;
-        }
-        if ((uint32_t)(info[t + 1] & 63u) == end) break;
-        q = end;
-    }
-    L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
-    return true;
-}
-
-__global__ void dec_fix_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
-                               unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                               unsigned long long nch, const unsigned long long *gate)
-{
-    if (gate && !(*gate & DF_GATE_MASK)) return;
-    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (c >= nch || tab->single_sym) return;
-    DecLayout L(work, nch);
-    uint32_t s = L.chunkE[c - 1];
-    if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
-    TabView T{tab->t1, tab->t2, tab->longs, tab->n_long};
-    uint32_t bad = 0;
-    if (!fix_chunk(T, frame, frame_bytes, range_end_bit, work, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
-    if (bad) atomicExch(&work->flags[1], 1ull);
-}
-
-// streams that do not synchronise within a whole chunk: carry the true start forward serially
-__global__ void dec_fix_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
-                                      unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
-                                      DecWork *work, unsigned long long nch, const unsigned long long *gate)
-{
-    if (gate && !(*gate & DF_GATE_MASK)) return;
-    if (work->flags[0] == 0 || tab->single_sym) return;
-    DecLayout L(work, nch);
-    TabView T{tab->t1, tab->t2, tab->longs, tab->n_long};
-    uint32_t bad = 0;
-    for (unsigned long long c = 1; c < nch; c++) {
-        if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix_kernel used
-        uint32_t s = L.chunkE2[c - 1];
-        if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
-        fix_chunk(T, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
-    }
-    if (bad) atomicExch(&work->flags[1], 1ull);
-}
-
 // Exclusive scan of the chunk symbol counts -> chunkBase, in three small steps: every block of 4096 chunks scans
 // itself (dec_scan1_kernel), one CTA scans the block totals (dec_scan2_kernel), dec_scan3_kernel adds them back.
 constexpr uint32_t DSCAN_PER_BLOCK = 4096;
 
 __global__ void __launch_bounds__(1024)
 dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
-                 unsigned long long *block_tot, const unsigned long long *gate)
+                 unsigned long long *block_tot)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     __shared__ unsigned long long s_w[33];
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -561,9 +327,8 @@ dec_scan1_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, u
 }
 
 __global__ void __launch_bounds__(1024)
-dec_scan2_kernel(DecWork *work, unsigned long long *block_tot, uint32_t nblocks, const unsigned long long *gate)
+dec_scan2_kernel(DecWork *work, unsigned long long *block_tot, uint32_t nblocks)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     __shared__ unsigned long long s_w[33];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t per = (nblocks + 1023) / 1024;
@@ -593,9 +358,8 @@ dec_scan2_kernel(DecWork *work, unsigned long long *block_tot, uint32_t nblocks,
 
 __global__ void __launch_bounds__(1024)
 dec_scan3_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
-                 const unsigned long long *block_tot, const unsigned long long *gate)
+                 const unsigned long long *block_tot)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     DecLayout L(work, nch);
     const unsigned long long add = block_tot[blockIdx.x];
     if (add == 0) return;
@@ -603,83 +367,6 @@ dec_scan3_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, u
         const unsigned long long i = c0 + (unsigned long long)blockIdx.x * DSCAN_PER_BLOCK + j;
         if (i < c1) L.chunkBase[i] += add;
     }
-}
-
-__global__ void __launch_bounds__(DEC_THREADS)
-dec_write_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
-                 const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                 unsigned long long n_symbols, uint16_t *__restrict__ out, const unsigned long long *gate)
-{
-    if (gate && !(*gate & DF_GATE_MASK)) return;
-    extern __shared__ __align__(16) uint32_t dyn_smem[];
-    uint32_t *sw = dyn_smem;                                        // CHUNK_WORDS + CHUNK_PAD_WORDS
-    uint32_t *st1 = sw + SW_PADDED;                                 // 2^K1
-    uint16_t *sout = reinterpret_cast<uint16_t *>(st1 + (1u << K1)); // WIN_SYMS + 8
-    __shared__ uint32_t s_w[33];
-    if (tab->single_sym) return;
-    DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned long long c = blockIdx.x;
-    const unsigned long long base = L.chunkBase[c];
-    if (base >= n_symbols) return;
-    for (uint32_t i = tid; i < (1u << K1); i += DEC_THREADS) st1[i] = tab->t1[i];
-    stage_chunk(sw, frame, frame_bytes, c);
-
-    const uint32_t inf = L.info[c * DEC_THREADS + tid];
-    const uint32_t p = (c == 0 && tid == 0) ? (uint32_t)F0 : (inf & 63u);   // the stream head may sit past bit 63
-    uint32_t remaining = inf >> 6;
-    // exclusive scan of the counts inside the chunk
-    uint32_t x = remaining;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_w[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t s = lane < DEC_THREADS / 32 ? s_w[lane] : 0u, t = s;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
-        if (lane < DEC_THREADS / 32) s_w[lane] = t - s;
-        if (lane == 31) s_w[32] = t;
-    }
-    __syncthreads();
-    uint32_t next = x - remaining + s_w[wid];           // chunk-relative index of my next symbol
-    unsigned long long total = s_w[32];
-    if (base + total > n_symbols) total = n_symbols - base;   // garbage past the payload end is dropped
-
-    TabView T{st1, tab->t2, tab->longs, tab->n_long};
-    SmemFetch f{sw};
-    BitReader<SmemFetch> r{f};
-    const uint32_t sub_bit0 = tid * SUB_BITS;
-    r.init(sub_bit0 + p);
-    uint32_t pos = p, bad = 0;
-
-    const uint32_t mis = (uint32_t)(base & 7);          // staging slot j <-> output symbol base - mis + j
-    for (unsigned long long w0 = 0; w0 < total; w0 += WIN_SYMS) {
-        const unsigned long long wend = min(total, w0 + WIN_SYMS);
-        while (remaining && next < wend) {
-            uint32_t e = decode_one(T, r, sub_bit0 + pos, bad);
-            uint32_t len = e & 0x7Fu;
-            sout[next - (uint32_t)w0 + mis] = (uint16_t)(e >> 8);
-            pos += len;
-            r.skip(len);
-            next++; remaining--;
-        }
-        if (remaining && next >= total) remaining = 0;
-        __syncthreads();
-        // flush [w0, wend): staging slots [mis, mis + n)
-        const uint32_t n = (uint32_t)(wend - w0);
-        uint16_t *dst = out + base + w0 - mis;          // 16-byte aligned when out is
-        const uint32_t nvec = (mis + n + 7) / 8;
-        for (uint32_t q = tid; q < nvec; q += DEC_THREADS) {
-            const uint32_t j0 = q * 8;
-            if (j0 >= mis && j0 + 8 <= mis + n && (((uintptr_t)(dst + j0) & 15) == 0)) {
-                st_stream_v4(dst + j0, reinterpret_cast<const uint4 *>(sout)[q]);
-            } else {
-                for (uint32_t j = j0; j < j0 + 8; j++)
-                    if (j >= mis && j < mis + n) dst[j] = sout[j];
-            }
-        }
-        __syncthreads();
-    }
-    if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
 // U == 1 with a zero-length code: the payload is empty, every symbol is the same
@@ -697,21 +384,14 @@ __global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned lo
 int launch_table_planes(Ctx *c, DecodeTable *d_tab);             // decode2.cu
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c0, unsigned long long c1, bool tail_only, const unsigned long long *gate);
+                 unsigned long long c0, unsigned long long c1, bool tail_only);
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, const unsigned long long *gate);
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out);
 
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
                 const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                unsigned long long c1, const unsigned long long *gate);
-
-static bool use_old_kernels()
-{   // development switch: HF_DECODE_OLD=1 runs decode.cu's first-generation kernels (A/B timing)
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("HF_DECODE_OLD"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
+                unsigned long long c1);
 
 static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
 {
@@ -757,69 +437,36 @@ int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, Deco
     return build_tables(c, src, d_tab);
 }
 
-size_t df_work_bytes(unsigned long long nch);                   // decode_fast.cu
-unsigned long long df_chunks(unsigned long long range_end_bit);
-int launch_decode_fast(Ctx *c, const uint8_t *frame, long long hi_valid, long long range_end_bit, uint32_t F0,
-                       unsigned long long out_limit, const DecodeTable *d_tab, uint16_t *out, void *work_mem,
-                       unsigned long long nch, bool tail_only);
-
-// the exact kernels; gate == nullptr runs them unconditionally, otherwise only when the single-pass
-// decoder raised one of DF_GATE_MASK (decided on the device: hf_decode stays asynchronous)
 // the scan of the chunk counts of [c0, c1); work->result[2] carries the symbols before c0 in and those before c1 out
-static int launch_scan(Ctx *c, DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1,
-                       const unsigned long long *gate)
+static int launch_scan(Ctx *c, DecWork *work, unsigned long long nch, unsigned long long c0, unsigned long long c1)
 {
     if (c1 <= c0) return HF_OK;
     const uint32_t nblocks = (uint32_t)((c1 - c0 + DSCAN_PER_BLOCK - 1) / DSCAN_PER_BLOCK);
     unsigned long long *block_tot = reinterpret_cast<unsigned long long *>(c->d_scan);
     if (nblocks > SCAN_BLOCKS_MAX) return set_err(c, HF_ERR_ARG, "hf_decode: stream too large");
-    HF_PROF(c, "dec_scan1_kernel"); dec_scan1_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot, gate);
+    HF_PROF(c, "dec_scan1_kernel"); dec_scan1_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_scan2_kernel"); dec_scan2_kernel<<<1, 1024, 0, c->stream>>>(work, block_tot, nblocks, gate);
+    HF_PROF(c, "dec_scan2_kernel"); dec_scan2_kernel<<<1, 1024, 0, c->stream>>>(work, block_tot, nblocks);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_scan3_kernel"); dec_scan3_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot, gate);
+    HF_PROF(c, "dec_scan3_kernel"); dec_scan3_kernel<<<nblocks, 1024, 0, c->stream>>>(work, nch, c0, c1, block_tot);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
-// The exact kernels over the chunks [c0, c1) of the frame: the whole stream in one go, or one slice of a pipelined
-// host-buffer decode (slices in order; c0 a multiple of 2).  gate == nullptr runs them unconditionally, otherwise
-// only when the single-pass decoder raised one of DF_GATE_MASK (decided on the device: hf_decode stays asynchronous).
+// The decode kernels over the chunks [c0, c1) of the frame: the whole stream in one go, or one slice of a pipelined
+// host-buffer decode (slices in ascending order; c0 a multiple of 2).
 static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                                unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
                                uint16_t *out16, DecWork *work, unsigned long long nch, unsigned long long c0,
-                               unsigned long long c1, const unsigned long long *gate)
+                               unsigned long long c1)
 {
-    int rc;
-    if (!use_old_kernels()) {
-        rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false, gate);
-        if (rc) return rc;
-        rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
-        if (rc) return rc;
-        rc = launch_scan(c, work, nch, c0, c1, gate);
-        if (rc) return rc;
-        return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16, gate);
-    }
-    // HF_DECODE_OLD=1: the first-generation kernels, whole stream only
-    HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<(unsigned)nch, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, 0, 0u, gate);
-    HF_LAUNCH_CHECK(c);
-    if (nch > 1) {
-        HF_PROF(c, "dec_fix_kernel"); dec_fix_kernel<<<(unsigned)((nch - 1 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
-        HF_LAUNCH_CHECK(c);
-        HF_PROF(c, "dec_fix_serial_kernel"); dec_fix_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, gate);
-        HF_LAUNCH_CHECK(c);
-    }
-    rc = launch_scan(c, work, nch, 0, nch, gate);
+    int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false);
     if (rc) return rc;
-    const size_t wsmem = (SW_PADDED + (1u << K1)) * 4 + (WIN_SYMS + 8) * 2;
-    static bool wattr = false;
-    if (!wattr) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-        wattr = true;
-    }
-    HF_PROF(c, "dec_write_kernel"); dec_write_kernel<<<(unsigned)nch, DEC_THREADS, wsmem, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, n_symbols, out16, gate);
-    HF_LAUNCH_CHECK(c);
-    return HF_OK;
+    rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
+    if (rc) return rc;
+    rc = launch_scan(c, work, nch, c0, c1);
+    if (rc) return rc;
+    return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16);
 }
 
 // A decode of one stream, all at once (launch_decode) or in slices of chunks as its bytes arrive from the host
@@ -844,13 +491,10 @@ int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_
     job->n_symbols = n_symbols;
     job->tab = d_tab;
     job->out16 = reinterpret_cast<uint16_t *>(d_out);
-    const unsigned long long nch_fast = df_chunks(job->frame_bytes * 8);
     const size_t off = 8u << 20;                        // behind the table-source / codebook workspace
-    const size_t exact_bytes = (DecLayout::bytes(job->nch) + 255) & ~(size_t)255;
-    int rc = ensure_ws(c, off + exact_bytes + df_work_bytes(nch_fast));
+    int rc = ensure_ws(c, off + DecLayout::bytes(job->nch));
     if (rc) return rc;
     job->work = (uint8_t *)c->ws + off;
-    job->fast_work = (uint8_t *)c->ws + off + exact_bytes;
     job->total = reinterpret_cast<unsigned long long *>(job->work) + 2;     // DecWork::result[2]
     HF_CUDA(c, cudaMemsetAsync(job->work, 0, sizeof(DecWork), c->stream));
     HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, job->out16);
@@ -861,7 +505,7 @@ int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_
 int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned long long c1)
 {
     return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, job.n_symbols, job.tab, job.out16,
-                               reinterpret_cast<DecWork *>(job.work), job.nch, c0, c1, nullptr);
+                               reinterpret_cast<DecWork *>(job.work), job.nch, c0, c1);
 }
 
 int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,
@@ -871,15 +515,7 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
     DecodeJob job;
     int rc = decode_begin(c, d_stream, stream_bytes, start_bit, n_symbols, d_tab, d_out, &job);
     if (rc) return rc;
-    const unsigned long long *gate = nullptr;
-    if (!c->decode_exact_only) {
-        rc = launch_decode_fast(c, job.frame, (long long)job.frame_bytes, (long long)(job.frame_bytes * 8), (uint32_t)job.F0,
-                                n_symbols, d_tab, job.out16, job.fast_work, df_chunks(job.frame_bytes * 8), false);
-        if (rc) return rc;
-        gate = reinterpret_cast<const unsigned long long *>((uint8_t *)job.fast_work + 16) + 3;     // DfWork::result[3]
-    }
-    return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, n_symbols, d_tab, job.out16,
-                               reinterpret_cast<DecWork *>(job.work), job.nch, 0, job.nch, gate);
+    return decode_slice(c, job, 0, job.nch);
 }
 
 // result[4] of a range call from the exact kernels' work area: -, overflow, symbols, flags
@@ -911,40 +547,23 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
     if (nch == 0) nch = 1;
     if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode_range: range too large");
     const size_t off = 8u << 20;
-    if (!c->decode_exact_only && !tail_only) {          // the single-pass kernel (hf_set_decode_mode(ctx, 0))
-        const unsigned long long nchf = df_chunks(end_bit);
-        int rc = ensure_ws(c, off + df_work_bytes(nchf));
-        if (rc) return rc;
-        void *fast_work = (uint8_t *)c->ws + off;
-        rc = launch_decode_fast(c, frame, (long long)frame_bytes, (long long)end_bit, (uint32_t)F0, out_symbols, d_tab,
-                                reinterpret_cast<uint16_t *>(d_out), fast_work, nchf, false);
-        if (rc) return rc;
-        HF_CUDA(c, cudaMemcpyAsync(d_result, (uint8_t *)fast_work + 16, 32, cudaMemcpyDeviceToDevice, c->stream));
-        return HF_OK;
-    }
     int rc = ensure_ws(c, off + DecLayout::bytes(nch));
     if (rc) return rc;
     DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
     HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
     if (tail_only) {
-        // only the last chunk, from a guessed start: 16 KiB of self-synchronisation lie before the range end
-        if (use_old_kernels()) {
-            HF_PROF(c, "dec_sync_kernel"); dec_sync_kernel<<<1, DEC_THREADS, 0, c->stream>>>(frame, frame_bytes, F0, end_bit, d_tab, work, nch, nch - 1, 1u, nullptr);
-            HF_LAUNCH_CHECK(c);
-        } else {
-            rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true, nullptr);
-            if (rc) return rc;
+        rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true);
+        if (rc) return rc;
+        {
             // the (up to) 8 groups of the tail converge one by one on guessed starts; the repair carries the chain
             // from the first of them (the lead-in, 224 KiB or more when the range is that long) to the range end
             const unsigned long long ngroups = (nch + 1) / 2, g_first = ngroups > 8 ? ngroups - 8 : 0;
-#ifndef HF_NO_TAIL_FIX
-            rc = launch_fix2(c, frame, frame_bytes, end_bit, d_tab, work, nch, g_first * 2 + 1, nch, nullptr);
+            rc = launch_fix2(c, frame, frame_bytes, end_bit, d_tab, work, nch, g_first * 2 + 1, nch);
             if (rc) return rc;
-#endif
         }
     } else {
         rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
-                                 work, nch, 0, nch, nullptr);
+                                 work, nch, 0, nch);
         if (rc) return rc;
     }
     HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, tail_only ? ~0ull >> 8 : out_symbols, d_result);

@@ -1,17 +1,17 @@
-// decode2.cu — the word-walk kernels of the exact decoder: dec_sync2_kernel (code word boundaries and
-// symbol counts per 256-bit subsequence) and dec_write2_kernel (symbols out).  They replace the two
-// hot kernels of decode.cu (dec_sync_kernel, dec_write_kernel) and keep their global interface
-// (DecLayout: info / chunkCnt / chunkE), so the inter-chunk repair and the scan of decode.cu stay.
+// decode2.cu — the hot kernels of the decoder: dec_sync3_kernel (code word boundaries and symbol counts per
+// 256-bit subsequence), dec_fix2_kernel (inter-group repair) and dec_write3_kernel (symbols out), plus the
+// shared-memory table planes they read.  decode.cu holds the header parser, the general tables, the scan and
+// the orchestration; the kernels meet in the work area of decode_common.cuh (DecLayout: info / chunkCnt / chunkE).
 //
 // The reference decodes on the host, one bit and one fread() per step, by chasing tree pointers
 // (/root/reference/Decompressor.cu:259-291); its format has no offset index.
 //
-// What is different from decode.cu's first kernels (ncu: 76 + 65 thread instructions per symbol, 39 %
-// of the lanes active in the synchronisation kernel, 55 % of the symbols of the 16 GiB bench stream
-// looked up in global memory):
-//   * a thread keeps its 256-bit subsequence (+ one look-ahead word) in REGISTERS, loaded straight
-//     from global memory; the walk is unrolled over the 8 words, so the 32-bit window of a code word
-//     is ONE funnel shift of two registers — no shared-memory staging of the payload, no bit reader;
+// Design notes (the first kernels of this round staged the payload per chunk, kept a 64-bit bit reader and a
+// 12-bit first-level table: ncu showed 76 + 65 thread instructions per symbol, 39 % of the lanes active and
+// 55 % of the symbols of the 16 GiB bench stream looked up in global memory):
+//   * the write kernel keeps a thread's 256-bit subsequence (+ one look-ahead word) in REGISTERS, loaded
+//     straight from global memory; the walk is unrolled over the words, so the 32-bit window of a code word
+//     is a funnel shift of two registers — no shared-memory staging of the payload, no bit reader;
 //   * the table of the hot loop is ONE 64 KiB shared-memory plane indexed by 14 bits whose entries are either a
 //     code word of at most 14 bits or a "micro tree": the shape (16-bit leaf-start mask) of the complete
 //     depth-4 subtree below that prefix, from which the length of a 15..18-bit code is a few bit operations and
@@ -311,10 +311,8 @@ __device__ __forceinline__ bool team_or(uint32_t team, bool pred)
 __global__ void __launch_bounds__(S3_THREADS, 1)
 dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                 unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative,
-                 const unsigned long long *gate)
+                 unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;        // the single-pass decoder succeeded
     extern __shared__ __align__(16) uint32_t s3_smem[];
     uint32_t *s_t14 = s3_smem;                          // 2^MICRO_K
     uint32_t *s_bits = s3_smem + (1u << MICRO_K);       // S3_THREADS rows of ROW_WORDS
@@ -438,9 +436,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                   unsigned long long c0, unsigned long long c1, unsigned long long n_symbols,
-                  uint16_t *__restrict__ out, const unsigned long long *gate)
+                  uint16_t *__restrict__ out)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     extern __shared__ __align__(16) uint32_t w3_smem[];
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
     uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
@@ -654,10 +651,8 @@ __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigne
 
 __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                                unsigned long long nch, unsigned long long c0, unsigned long long c1,
-                                const unsigned long long *gate)
+                                unsigned long long nch, unsigned long long c0, unsigned long long c1)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     const unsigned long long c = c0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;    // c0 >= 1
     if (c >= c1 || tab->single_sym) return;
     DecLayout L(work, nch);
@@ -672,9 +667,8 @@ __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long
 __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                        unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
                                        DecWork *work, unsigned long long nch, unsigned long long c0,
-                                       unsigned long long c1, const unsigned long long *gate)
+                                       unsigned long long c1)
 {
-    if (gate && !(*gate & DF_GATE_MASK)) return;
     if (work->flags[0] == 0 || tab->single_sym) return;
     DecLayout L(work, nch);
     uint32_t bad = 0;
@@ -690,13 +684,13 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
 // chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
                 const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                unsigned long long c1, const unsigned long long *gate)
+                unsigned long long c1)
 {
     if (c0 == 0) c0 = 1;
     if (c1 <= c0) return HF_OK;
-    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((c1 - c0 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
+    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((c1 - c0 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, gate);
+    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -705,7 +699,7 @@ int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, un
 // chunks [c0, c1), c0 a multiple of GROUP_CHUNKS; tail_only ignores the range
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c0, unsigned long long c1, bool tail_only, const unsigned long long *gate)
+                 unsigned long long c0, unsigned long long c1, bool tail_only)
 {
     static bool attr = false;
     if (!attr) {
@@ -726,14 +720,14 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_sync3_kernel");
     dec_sync3_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
-                                                                       g_first, ngroups, tail_only ? 1u : 0u, gate);
+                                                                       g_first, ngroups, tail_only ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, const unsigned long long *gate)
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out)
 {
     if (c1 <= c0) return HF_OK;
     static bool attr = false;
@@ -744,7 +738,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     unsigned long long grid = ((c1 - c0) * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, gate);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

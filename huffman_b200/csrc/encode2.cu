@@ -1,5 +1,4 @@
-// encode2.cu — warp-independent Huffman encoder (the default; encode.cu keeps the first, CTA-tiled version
-// behind HF_ENCODE_OLD=1 for A/B timing).
+// encode2.cu — warp-independent Huffman encoder.
 //
 // Replaces populateCWLength + thrust::transform_inclusive_scan + encodeFromCW + the host tail flush
 // (/root/reference/Compressor.cu:50-74, :152-313, :541-601, :673-684): the reference materialises 12 bytes of
@@ -24,8 +23,6 @@
 // C:541, C:294-310); the last byte is zero padded (C:597-601).
 //
 // Algorithmic bytes: N read + C written (traffic 2N + C + N/128).  Roofline: HBM; today issue / LSU bound.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace hf {
@@ -505,16 +502,10 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
     }
 }
 
-int launch_encode_old(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
-                      uint64_t start_bit, uint32_t maxlen_hint);         // encode.cu
-
 int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
                   uint64_t start_bit, uint32_t maxlen_hint)
 {
-    static int use_old = -1;
-    if (use_old < 0) { const char *e = getenv("HF_ENCODE_OLD"); use_old = (e && e[0] == '1') ? 1 : 0; }
-    if (use_old) return launch_encode_old(c, d_in, n_bytes, d_cb, d_stream, start_bit, maxlen_hint);
-
+    (void)maxlen_hint;
     const uint64_t n_sym = n_bytes / 2;
     if (n_sym == 0) return HF_OK;
     if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
