@@ -327,10 +327,11 @@ def run_ours(args):
     dom = next(iter(kern)) if kern else None
     roof = None
     if dom and "gbs" in kern[dom]:
-        traffic = None
+        traffic = None          # dram bytes per launch from the ncu --set full capture, scaled to this shard
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom.split("<")[0])
+            per_byte = json.load(open(tp)).get("per_input_byte", {}).get(dom)
+            traffic = per_byte * n_shard if per_byte is not None else None
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"]}
