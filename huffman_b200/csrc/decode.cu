@@ -6,10 +6,10 @@
 // by itself.
 //
 // Header (dec_parse_kernel): entry k+1 starts 24+len_k bits after entry k — a serial chain.
-//   One warp chases it SPECULATIVELY from shared-memory staging: lane j assumes the next
-//   entries keep the current stride and reads the length of entry k+j; the ballot of the
-//   first mismatch confirms up to 32 entries per step (the table is sorted by count, so
-//   lengths come in long runs).  Any header parses correctly, sorted ones ~32x faster.
+//   One CTA chases it SPECULATIVELY from shared-memory staging: thread i assumes the next
+//   entries keep the current stride and reads the length of entry k+i; the first mismatch
+//   confirms up to 1024 entries per step (the table is sorted by count, so lengths come in
+//   long runs).  Any header parses correctly, sorted ones ~1000x faster than entry by entry.
 //
 // Tables (dt_*): a general two-level table for any code length up to 64 bits (12-bit primary, per-prefix
 //   secondary tables of up to +12 bits, a linear list for still longer codes); decode2.cu derives the
@@ -161,7 +161,6 @@ __device__ __forceinline__ uint32_t hdr_byte_at_bit(const uint8_t *sm, uint32_t 
 }
 
 constexpr uint32_t HDR_STAGE = 64 * 1024;               // staged header bytes
-constexpr uint32_t HDR_MARGIN = 32 * 280 / 8 + 64;      // a full speculative step must fit: 32 entries of <= 24+255 bits
 
 __global__ void __launch_bounds__(1024, 1)
 dec_parse_kernel(const uint8_t *__restrict__ file, unsigned long long file_bytes, TabSrc *__restrict__ src,
@@ -187,43 +186,49 @@ dec_parse_kernel(const uint8_t *__restrict__ file, unsigned long long file_bytes
     if (tid == 0) { s_pos = 0; s_k = 0; s_done = (U == 0 || !ok); s_err = !ok; }
     __syncthreads();
 
+    __shared__ uint32_t s_first;                        // first entry of a step that is not where the stride predicts
     while (!s_done) {
         // stage HDR_STAGE bytes starting at the byte holding s_pos
         const unsigned long long b0 = s_pos >> 3;
         for (uint32_t i = tid; i < HDR_STAGE + 16; i += 1024)
             sm[i] = (b0 + i < stream_bytes) ? stream[b0 + i] : 0;
         __syncthreads();
-        if (tid < 32) {
-            unsigned long long pos = s_pos;
-            uint32_t k = s_k;
-            uint32_t stride = 0;
-            bool err = false;
-            while (k < U) {
-                uint32_t rel = (uint32_t)(pos - b0 * 8);
-                if ((rel >> 3) + HDR_MARGIN > HDR_STAGE) break;       // restage
-                if ((pos >> 3) + 3 > stream_bytes) { err = true; break; }
-                if (stride == 0) stride = 24 + hdr_byte_at_bit(sm, rel + 16);
-                uint32_t myrel = rel + lane * stride;
-                uint32_t L = hdr_byte_at_bit(sm, myrel + 16);
-                uint32_t mism = __ballot_sync(0xFFFFFFFFu, 24 + L != stride);
-                uint32_t f = mism ? (uint32_t)__ffs(mism) - 1 : 32u;  // entries 0..f sit at their predicted places
-                uint32_t n_ok = min(f + 1, 32u);
-                n_ok = min(n_ok, U - k);
-                if (lane < n_ok) {
-                    src->entry_pos[k + lane] = pos + (unsigned long long)lane * stride;
-                    src->len[k + lane] = L;
-                }
-                // advance past the confirmed entries
-                uint32_t Lf = __shfl_sync(0xFFFFFFFFu, L, n_ok - 1);
-                pos += (unsigned long long)(n_ok - 1) * stride + 24 + Lf;
-                k += n_ok;
-                stride = 24 + Lf;
+        // Steps of up to 1024 entries: thread i assumes the entries keep the stride of the first one and reads the
+        // length of entry k + i at its predicted place; everything before the first mismatch is confirmed at once.
+        for (;;) {
+            const unsigned long long pos = s_pos;
+            const uint32_t k = s_k;
+            if (k >= U) { if (tid == 0) s_done = 1; break; }
+            const uint32_t rel = (uint32_t)(pos - b0 * 8);
+            if ((rel >> 3) + 64 > HDR_STAGE) break;                     // restage
+            if ((pos >> 3) + 3 > stream_bytes) { if (tid == 0) { s_err = 1; s_done = 1; } break; }
+            const uint32_t stride = 24 + hdr_byte_at_bit(sm, rel + 16);
+            uint32_t n_can = (HDR_STAGE * 8 - 64 - rel) / stride;      // entries whose length byte is staged
+            if (n_can < 32 && (rel >> 3) > 1024) break;                // a short step near the end of the stage: restage
+            n_can = min(min(n_can, 1024u), U - k);
+            if (tid == 0) s_first = n_can;
+            __syncthreads();
+            uint32_t L = 0;
+            if (tid < n_can) {
+                const uint32_t myrel = rel + tid * stride;
+                const bool inb = ((pos + (unsigned long long)tid * stride) >> 3) + 3 <= stream_bytes;
+                L = inb ? hdr_byte_at_bit(sm, myrel + 16) : 0xFFFFFFFFu;    // out of the stream: never matches
+                if (24 + L != stride) atomicMin(&s_first, tid);
             }
-            if (lane == 0) {
-                s_pos = pos; s_k = k;
-                if (err) { s_err = 1; s_done = 1; }
-                if (k >= U) s_done = 1;
+            __syncthreads();
+            const uint32_t f = s_first;                                 // entries 0 .. f sit at their predicted places
+            const uint32_t n_ok = min(f + 1, n_can);
+            if (tid < n_ok && L != 0xFFFFFFFFu) {
+                src->entry_pos[k + tid] = pos + (unsigned long long)tid * stride;
+                src->len[k + tid] = L;
             }
+            if (tid == n_ok - 1) {
+                if (L == 0xFFFFFFFFu) { s_err = 1; s_done = 1; }        // an entry that is needed lies past the stream
+                s_pos = pos + (unsigned long long)tid * stride + 24 + L;
+                s_k = k + n_ok;
+            }
+            __syncthreads();
+            if (s_done) break;
         }
         __syncthreads();
     }
