@@ -362,9 +362,21 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
         uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
         uint32_t end = 0;
         Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
+        // `rec` describes the walk from rec_p, which ended at rec_end.  memo: up to four (start + 1, end) pairs of
+        // walks this thread has done on this span.  Data that does not re-synchronise (a long run of one code word
+        // is periodic: a walk that enters it out of phase leaves it out of phase) makes the fix-point hand a lane
+        // the same few starts again and again; a remembered start costs no walk, and the record of the final start
+        // is rebuilt once at the end.
+        uint32_t rec_p = p, rec_end = 0, mslot = 0;
+        unsigned long long memo = 0;
+        auto memo_add = [&](uint32_t st, uint32_t en) {
+            memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((st + 1) << 8) | en) << (16 * mslot));
+            mslot = (mslot + 1) & 3;
+        };
         if (lim) {
-            if (p < lim) walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            if (p < lim) { walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
             else end = p - lim;
+            rec_end = end;
         }
         // Fix-point: my true start is my predecessor's overflow.  Inside a warp the overflows travel by
         // shuffle and the warps iterate on their own; the warps then exchange their last overflow through
@@ -378,8 +390,23 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
                 const bool need = movable && q != p;
                 if (!__any_sync(0xFFFFFFFFu, need)) break;
                 if (need) {
-                    if (q < lim) walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
-                    else { rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim; }
+                    uint32_t hit = 0;                   // ((q + 1) << 8) | end of a walk from q done before
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
+                        if ((en >> 8) == q + 1) hit = en;
+                    }
+                    if (hit) {
+                        end = hit & 0xFFu;              // rec stays with the walk it describes
+                    } else if (q < lim) {
+                        end = rec_end;                  // a merge keeps the recorded walk's end
+                        walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                        rec_p = q; rec_end = end;
+                        memo_add(q, end);
+                    } else {
+                        rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim;
+                        rec_p = q; rec_end = end;
+                    }
                     p = q;
                 }
             }
@@ -387,6 +414,14 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
             team_sync(team);
             q0 = (tt >> 5) ? s_wend[wid - 1] : p;
             if (!team_or(team, lane == 0 && movable && q0 != p)) break;
+        }
+        if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
+            if (p < lim) {
+                end = rec_end;
+                walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            } else {
+                rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
+            }
         }
 
         // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
