@@ -394,9 +394,9 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
                   unsigned long long c1, unsigned long long n_symbols, uint16_t *out);
 
-int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
-                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                unsigned long long c1);
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+                unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
+                unsigned long long c0, unsigned long long c1, bool speculative);
 
 static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
 {
@@ -467,7 +467,7 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
 {
     int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false);
     if (rc) return rc;
-    rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
+    rc = launch_fix2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false);
     if (rc) return rc;
     rc = launch_scan(c, work, nch, c0, c1);
     if (rc) return rc;
@@ -563,7 +563,7 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
             // the (up to) 8 groups of the tail converge one by one on guessed starts; the repair carries the chain
             // from the first of them (the lead-in, 224 KiB or more when the range is that long) to the range end
             const unsigned long long ngroups = (nch + 1) / 2, g_first = ngroups > 8 ? ngroups - 8 : 0;
-            rc = launch_fix2(c, frame, frame_bytes, end_bit, d_tab, work, nch, g_first * 2 + 1, nch);
+            rc = launch_fix2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, (g_first + 1) * 2, nch, true);
             if (rc) return rc;
         }
     } else {

@@ -308,6 +308,160 @@ __device__ __forceinline__ bool team_or(uint32_t team, bool pred)
     return r != 0;
 }
 
+// what the threads of a synchronisation CTA share
+struct SyncCtx {
+    const uint8_t *frame;
+    unsigned long long frame_bytes, F0, range_end_bit, nch;
+    const DecodeTable *tab;
+    DecWork *work;
+    const uint32_t *s_t14;
+    uint32_t *s_bits, *s_wend, *s_red;
+    uint32_t g, k2shift;                // gcd of the code lengths (1 when speculating), 32 - k2
+};
+
+// One team converges on one group (2 chunks, 32 KiB): per-subsequence records, chunk totals and overflows.
+// exact: the group's first code word starts `start` bits into it (the stream head, or the true overflow of the group
+// before when a group is redone); otherwise the first span starts from a guess like every other one.
+__device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long grp, bool exact, uint32_t start, uint32_t &bad)
+{
+    const uint8_t *frame = S.frame;
+    const unsigned long long frame_bytes = S.frame_bytes, F0 = S.F0, range_end_bit = S.range_end_bit, nch = S.nch;
+    const DecodeTable *tab = S.tab;
+    DecWork *work = S.work;
+    const uint32_t *s_t14 = S.s_t14;
+    uint32_t *s_bits = S.s_bits, *s_wend = S.s_wend, *s_red = S.s_red;
+    const uint32_t g = S.g, k2shift = S.k2shift;
+    DecLayout L(work, nch);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t team = tid / TEAM_THREADS, tt = tid % TEAM_THREADS;      // my team, my index in it
+    const uint32_t *row = s_bits + tid * ROW_WORDS;
+    uint32_t *team_rows = s_bits + team * TEAM_THREADS * ROW_WORDS;
+
+    team_sync(team);                                // my team's rows, s_wend, s_red are free again
+    // ---- stage the group's 32 KiB: 8 coalesced 128-bit loads per thread ----
+    const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
+#pragma unroll
+    for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
+        const uint32_t v = tt + k * TEAM_THREADS;   // 16-byte vector of the group
+        const unsigned long long b = gbyte0 + 16ull * v;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (b < frame_bytes) x = ld_stream_v4(frame + b);          // the frame is 16-byte aligned
+        uint32_t *dst = team_rows + (v >> 3) * ROW_WORDS + 4 * (v & 7);
+        dst[0] = bswap32(x.x); dst[1] = bswap32(x.y); dst[2] = bswap32(x.z); dst[3] = bswap32(x.w);
+    }
+    {   // the pad word of my row: the first word of the next span
+        const unsigned long long b = gbyte0 + (unsigned long long)(tt + 1) * (SPAN_BITS / 8);
+        uint32_t x = 0;
+        if (b < frame_bytes) x = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b)));
+        s_bits[tid * ROW_WORDS + SPAN_WORDS] = x;
+    }
+    team_sync(team);
+
+    const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tt * SPAN_BITS;
+    const uint32_t lim = span_limit(X, range_end_bit);     // code words starting at or after the range end are not ours
+    const bool fixed = exact && tt == 0;                    // exact: the group's first code word starts at `start`
+    uint32_t p = fixed ? start : (X >= F0 ? spec_start(X, F0, g) : 0u);
+    uint32_t end = 0;
+    Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
+    // `rec` describes the walk from rec_p, which ended at rec_end.  memo: up to four (start + 1, end) pairs of
+    // walks this thread has done on this span.  Data that does not re-synchronise (a long run of one code word
+    // is periodic: a walk that enters it out of phase leaves it out of phase) makes the fix-point hand a lane
+    // the same few starts again and again; a remembered start costs no walk, and the record of the final start
+    // is rebuilt once at the end.
+    uint32_t rec_p = p, rec_end = 0, mslot = 0;
+    unsigned long long memo = 0;
+    auto memo_add = [&](uint32_t st, uint32_t en) {
+        memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((st + 1) << 8) | en) << (16 * mslot));
+        mslot = (mslot + 1) & 3;
+    };
+    if (lim) {
+        if (p < lim) { walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
+        else end = p - lim;
+        rec_end = end;
+    }
+    // Fix-point: my true start is my predecessor's overflow.  Inside a warp the overflows travel by
+    // shuffle and the warps iterate on their own; the warps then exchange their last overflow through
+    // shared memory, which usually moves only lane 0 of each warp.
+    const bool movable = !fixed && lim != 0;
+    uint32_t q0 = p;                                // lane 0's start: the guess, then the previous warp's overflow
+    for (uint32_t round = 0; round < TEAM_THREADS / 32 + 2; round++) {
+        for (;;) {
+            uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
+            if (lane == 0) q = q0;
+            const bool need = movable && q != p;
+            if (!__any_sync(0xFFFFFFFFu, need)) break;
+            if (need) {
+                uint32_t hit = 0;                   // ((q + 1) << 8) | end of a walk from q done before
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
+                    if ((en >> 8) == q + 1) hit = en;
+                }
+                if (hit) {
+                    end = hit & 0xFFu;              // rec stays with the walk it describes
+                } else if (q < lim) {
+                    end = rec_end;                  // a merge keeps the recorded walk's end
+                    walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                    rec_p = q; rec_end = end;
+                    memo_add(q, end);
+                } else {
+                    rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim;
+                    rec_p = q; rec_end = end;
+                }
+                p = q;
+            }
+        }
+        if (lane == 31) s_wend[wid] = end;
+        team_sync(team);
+        q0 = (tt >> 5) ? s_wend[wid - 1] : p;
+        if (!team_or(team, lane == 0 && movable && q0 != p)) break;
+    }
+    if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
+        if (p < lim) {
+            end = rec_end;
+            walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+        } else {
+            rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
+        }
+    }
+
+    // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
+    uint32_t cnt4[SPAN_SUBS];
+    uint32_t total = 0;
+    unsigned long long packed = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SPAN_SUBS; j++) {
+        const uint32_t pj = (rec.pos[j >> 1] >> (16 * (j & 1))) & 0xFFu;            // checkpoint 2j
+        const uint32_t cj = (rec.cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;          // segments 2j, 2j + 1
+        cnt4[j] = (cj & 0xFFu) + (cj >> 8);
+        total += cnt4[j];
+        packed |= (unsigned long long)((pj & 63u) | (cnt4[j] << 6)) << (16 * j);
+    }
+    const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tt * SPAN_SUBS;
+    if (sub_index < nch * DEC_THREADS)              // info holds whole chunks: 4 records never straddle its end
+        *reinterpret_cast<unsigned long long *>(L.info + sub_index) = packed;
+    // chunk totals: a chunk is 128 consecutive threads (4 warps)
+    uint32_t v = total;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) s_red[wid] = v;
+    team_sync(team);
+    constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
+    const unsigned long long c = grp * GROUP_CHUNKS + tt / TPC;
+    if (c < nch) {
+        if (tt % TPC == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < TPC / 32; i++) tot += s_red[wid + i];
+            L.chunkCnt[c] = tot;
+            L.chunkE2[c] = 0xFFFFFFFFu;
+        }
+        if (tt % TPC == TPC - 1) L.chunkE[c] = end;
+    }
+    // the thread whose span holds the end of the range reports the overflow past it
+    if (lim && span_limit(X + SPAN_BITS, range_end_bit) == 0) work->result[1] = end;
+}
+
 __global__ void __launch_bounds__(S3_THREADS, 1)
 dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                  unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
@@ -319,149 +473,89 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     __shared__ uint32_t s_wend[S3_THREADS / 32];
     __shared__ uint32_t s_red[S3_THREADS / 32];
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
-    DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t team = tid / TEAM_THREADS, tt = tid % TEAM_THREADS;      // my team, my index in it
+    const uint32_t tid = threadIdx.x, team = tid / TEAM_THREADS;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);       // lengths only
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
     }
-    const uint32_t g = speculative ? 1u : tab->len_gcd;
-    const uint32_t k2shift = 32u - tab->k2;
-    const uint32_t *row = s_bits + tid * ROW_WORDS;
-    uint32_t *team_rows = s_bits + team * TEAM_THREADS * ROW_WORDS;
+    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, s_t14, s_bits, s_wend, s_red,
+                    speculative ? 1u : tab->len_gcd, 32u - tab->k2};
     uint32_t bad = 0;
     __syncthreads();                                    // planes loaded
 
     for (unsigned long long grp = g_first + (unsigned long long)blockIdx.x * S3_TEAMS + team; grp < g_last;
-         grp += (unsigned long long)gridDim.x * S3_TEAMS) {
-        team_sync(team);                                // my team's rows, s_wend, s_red are free again
-        // ---- stage the group's 32 KiB: 8 coalesced 128-bit loads per thread ----
-        const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
-#pragma unroll
-        for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
-            const uint32_t v = tt + k * TEAM_THREADS;   // 16-byte vector of the group
-            const unsigned long long b = gbyte0 + 16ull * v;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (b < frame_bytes) x = ld_stream_v4(frame + b);          // the frame is 16-byte aligned
-            uint32_t *dst = team_rows + (v >> 3) * ROW_WORDS + 4 * (v & 7);
-            dst[0] = bswap32(x.x); dst[1] = bswap32(x.y); dst[2] = bswap32(x.z); dst[3] = bswap32(x.w);
-        }
-        {   // the pad word of my row: the first word of the next span
-            const unsigned long long b = gbyte0 + (unsigned long long)(tt + 1) * (SPAN_BITS / 8);
-            uint32_t x = 0;
-            if (b < frame_bytes) x = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b)));
-            s_bits[tid * ROW_WORDS + SPAN_WORDS] = x;
-        }
-        team_sync(team);
+         grp += (unsigned long long)gridDim.x * S3_TEAMS)
+        sync_group(S, grp, grp == 0 && !speculative, (uint32_t)F0, bad);
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
 
-        const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tt * SPAN_BITS;
-        const uint32_t lim = span_limit(X, range_end_bit);     // code words starting at or after the range end are not ours
-        const bool fixed = (grp == 0 && tt == 0 && !speculative);   // holds the first payload bit: exact start
-        uint32_t p = fixed ? (uint32_t)F0 : (X >= F0 ? spec_start(X, F0, g) : 0u);
-        uint32_t end = 0;
-        Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
-        // `rec` describes the walk from rec_p, which ended at rec_end.  memo: up to four (start + 1, end) pairs of
-        // walks this thread has done on this span.  Data that does not re-synchronise (a long run of one code word
-        // is periodic: a walk that enters it out of phase leaves it out of phase) makes the fix-point hand a lane
-        // the same few starts again and again; a remembered start costs no walk, and the record of the final start
-        // is rebuilt once at the end.
-        uint32_t rec_p = p, rec_end = 0, mslot = 0;
-        unsigned long long memo = 0;
-        auto memo_add = [&](uint32_t st, uint32_t en) {
-            memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((st + 1) << 8) | en) << (16 * mslot));
-            mslot = (mslot + 1) & 3;
-        };
-        if (lim) {
-            if (p < lim) { walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
-            else end = p - lim;
-            rec_end = end;
-        }
-        // Fix-point: my true start is my predecessor's overflow.  Inside a warp the overflows travel by
-        // shuffle and the warps iterate on their own; the warps then exchange their last overflow through
-        // shared memory, which usually moves only lane 0 of each warp.
-        const bool movable = !fixed && lim != 0;
-        uint32_t q0 = p;                                // lane 0's start: the guess, then the previous warp's overflow
-        for (uint32_t round = 0; round < TEAM_THREADS / 32 + 2; round++) {
-            for (;;) {
-                uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
-                if (lane == 0) q = q0;
-                const bool need = movable && q != p;
-                if (!__any_sync(0xFFFFFFFFu, need)) break;
-                if (need) {
-                    uint32_t hit = 0;                   // ((q + 1) << 8) | end of a walk from q done before
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
-                        if ((en >> 8) == q + 1) hit = en;
-                    }
-                    if (hit) {
-                        end = hit & 0xFFu;              // rec stays with the walk it describes
-                    } else if (q < lim) {
-                        end = rec_end;                  // a merge keeps the recorded walk's end
-                        walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
-                        rec_p = q; rec_end = end;
-                        memo_add(q, end);
-                    } else {
-                        rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim;
-                        rec_p = q; rec_end = end;
-                    }
-                    p = q;
-                }
-            }
-            if (lane == 31) s_wend[wid] = end;
-            team_sync(team);
-            q0 = (tt >> 5) ? s_wend[wid - 1] : p;
-            if (!team_or(team, lane == 0 && movable && q0 != p)) break;
-        }
-        if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
-            if (p < lim) {
-                end = rec_end;
-                walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
-            } else {
-                rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
-            }
-        }
+// Groups the cheap repair (dec_fix2_kernel) gave up on: the chain of the group before never meets the chain the
+// group recorded from its guessed start (data that does not re-synchronise, e.g. a long run of one code word).
+// A team takes the head of every run of such groups and redoes the groups one after the other from their TRUE
+// starts, walking on into the following groups for as long as the overflow it hands over is not the start they
+// recorded.  Runs are independent of each other; a chain that reaches another run's groups is caught by
+// dec_verify_kernel and settled by the serial kernel.
+constexpr uint32_t CHUNK_DIRTY = 0xFFFFFFFEu;           // in chunkE2 of a group's first chunk
 
-        // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
-        uint32_t cnt4[SPAN_SUBS];
-        uint32_t total = 0;
-        unsigned long long packed = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < SPAN_SUBS; j++) {
-            const uint32_t pj = (rec.pos[j >> 1] >> (16 * (j & 1))) & 0xFFu;            // checkpoint 2j
-            const uint32_t cj = (rec.cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;          // segments 2j, 2j + 1
-            cnt4[j] = (cj & 0xFFu) + (cj >> 8);
-            total += cnt4[j];
-            packed |= (unsigned long long)((pj & 63u) | (cnt4[j] << 6)) << (16 * j);
+__global__ void __launch_bounds__(S3_THREADS, 1)
+dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+                   unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                   unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative)
+{
+    if (work->flags[3] == 0) return;                    // no group was given up on
+    extern __shared__ __align__(16) uint32_t s3_smem[];
+    uint32_t *s_t14 = s3_smem;
+    uint32_t *s_bits = s3_smem + (1u << MICRO_K);
+    __shared__ uint32_t s_wend[S3_THREADS / 32];
+    __shared__ uint32_t s_red[S3_THREADS / 32];
+    if (tab->single_sym) return;
+    DecLayout L(work, nch);
+    const uint32_t tid = threadIdx.x, team = tid / TEAM_THREADS;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
+        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
+    }
+    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, s_t14, s_bits, s_wend, s_red,
+                    speculative ? 1u : tab->len_gcd, 32u - tab->k2};
+    uint32_t bad = 0;
+    __syncthreads();
+
+    const unsigned long long g_lo = g_first ? g_first : 1;      // the first group of a stream has an exact start
+    for (unsigned long long g = g_lo + (unsigned long long)blockIdx.x * S3_TEAMS + team; g < g_last;
+         g += (unsigned long long)gridDim.x * S3_TEAMS) {
+        // the head of a run: given up on, and the group before was not
+        if (L.chunkE2[g * GROUP_CHUNKS] != CHUNK_DIRTY) continue;
+        if (g > g_lo && L.chunkE2[(g - 1) * GROUP_CHUNKS] == CHUNK_DIRTY) continue;
+        for (unsigned long long cur = g;;) {
+            const uint32_t s = L.chunkE[cur * GROUP_CHUNKS - 1];    // final: the group before is settled
+            sync_group(S, cur, true, s, bad);                       // also resets chunkE2 of its chunks
+            team_sync(team);                                        // the group's records are in global memory
+            const unsigned long long next = cur + 1;
+            if (next >= g_last) break;
+            const bool dirty = L.chunkE2[next * GROUP_CHUNKS] == CHUNK_DIRTY;
+            const bool meets = L.chunkE[next * GROUP_CHUNKS - 1] == (uint32_t)(L.info[next * GROUP_CHUNKS * DEC_THREADS] & 63u);
+            if (!dirty && meets) break;
+            cur = next;
         }
-        const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tt * SPAN_SUBS;
-        if (sub_index < nch * DEC_THREADS)              // info holds whole chunks: 4 records never straddle its end
-            *reinterpret_cast<unsigned long long *>(L.info + sub_index) = packed;
-        // chunk totals: a chunk is 128 consecutive threads (4 warps)
-        uint32_t v = total;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) s_red[wid] = v;
-        team_sync(team);
-        constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
-        const unsigned long long c = grp * GROUP_CHUNKS + tt / TPC;
-        if (c < nch) {
-            if (tt % TPC == 0) {
-                uint32_t tot = 0;
-#pragma unroll
-                for (uint32_t i = 0; i < TPC / 32; i++) tot += s_red[wid + i];
-                L.chunkCnt[c] = tot;
-                L.chunkE2[c] = 0xFFFFFFFFu;
-            }
-            if (tt % TPC == TPC - 1) L.chunkE[c] = end;
-        }
-        // the thread whose span holds the end of the range reports the overflow past it
-        if (lim && span_limit(X + SPAN_BITS, range_end_bit) == 0) work->result[1] = end;
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
+
+// every group must start where the group before it ends; what the parallel repairs left open goes to the serial kernel
+__global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
+                                  unsigned long long g_first, unsigned long long g_last)
+{
+    const unsigned long long g = (g_first ? g_first : 1) + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_last || tab->single_sym) return;
+    DecLayout L(work, nch);
+    const unsigned long long c = g * GROUP_CHUNKS;
+    if (c >= nch) return;
+    if (L.chunkE[c - 1] != (uint32_t)(L.info[c * DEC_THREADS] & 63u)) atomicExch(&work->flags[0], 1ull);
+}
+
+
 
 // -------------------------------------------------------------------------------------------------
 // Every WARP works on its own: a unit of 32 consecutive subsequences (1 KiB of payload), whose output offset
@@ -649,8 +743,9 @@ __device__ __forceinline__ void sub_count(const DecodeTable *tab, const uint8_t 
     end = pos - lim;
 }
 
-// repairs chunk c from the true start `s` (offset inside the chunk's subsequence 0).
-// Returns true when the walk re-joined the recorded chain before the chunk ended.
+// repairs chunk c from the true start `s` (offset inside the chunk's subsequence 0): walks subsequence by
+// subsequence, rewriting the records, until the walk lands on a start the synchronisation kernel recorded.
+// Returns true when that happened before the chunk ended; otherwise chunkE[c] is the chunk's new overflow.
 __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigned long long frame_bytes,
                            unsigned long long range_end_bit, DecWork *work, DecLayout &L, unsigned long long c, uint32_t s,
                            uint32_t &bad)
@@ -673,8 +768,7 @@ __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigne
         }
         if (t + 1 == DEC_THREADS) {
             L.chunkCnt[c] = (uint32_t)((long long)L.chunkCnt[c] + delta);
-            const uint32_t curE = L.chunkE2[c] != 0xFFFFFFFFu ? L.chunkE2[c] : L.chunkE[c];
-            if (end != curE) { L.chunkE2[c] = end; return false; }
+            if (end != L.chunkE[c]) { L.chunkE[c] = end; return false; }
             return true;
         }
         if ((uint32_t)(info[t + 1] & 63u) == end) break;
@@ -684,21 +778,52 @@ __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigne
     return true;
 }
 
+// does a walk of chunk c from `s` land on a recorded start within FIX_PROBE subsequences?  (nothing is written)
+constexpr uint32_t FIX_PROBE = 16;
+__device__ bool probe_chunk(const DecodeTable *tab, const uint8_t *frame, unsigned long long frame_bytes,
+                            unsigned long long range_end_bit, DecLayout &L, unsigned long long c, uint32_t s, uint32_t &bad)
+{
+    const uint16_t *info = L.info + c * DEC_THREADS;
+    const uint32_t k2shift = 32u - tab->k2;
+    uint32_t q = s;
+    for (uint32_t t = 0; t < FIX_PROBE; t++) {
+        const uint32_t lim = sub_limit(c, t, range_end_bit);
+        if (lim == 0) return true;
+        uint32_t end, cnt;
+        sub_count(tab, frame, frame_bytes, c, t, q, lim, k2shift, end, cnt, bad);
+        if (sub_limit(c, t + 1, range_end_bit) == 0) return true;   // the range ends here
+        if ((uint32_t)(info[t + 1] & 63u) == end) return true;
+        q = end;
+    }
+    return false;
+}
+
+// One thread per group boundary (the chunks inside a group are consistent by construction).  Data that
+// re-synchronises meets the recorded chain after a subsequence or two; a group that does not within FIX_PROBE
+// subsequences is left to dec_regroup_kernel.
 __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                                unsigned long long nch, unsigned long long c0, unsigned long long c1)
+                                unsigned long long nch, unsigned long long g_first, unsigned long long g_last)
 {
-    const unsigned long long c = c0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;    // c0 >= 1
-    if (c >= c1 || tab->single_sym) return;
+    const unsigned long long g = (g_first ? g_first : 1) + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_last || tab->single_sym) return;
+    const unsigned long long c = g * GROUP_CHUNKS;
+    if (c >= nch) return;
     DecLayout L(work, nch);
     const uint32_t s = L.chunkE[c - 1];
     if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) return;
     uint32_t bad = 0;
-    if (!fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad)) atomicExch(&work->flags[0], 1ull);
-    if (bad) atomicExch(&work->flags[1], 1ull);
+    if (probe_chunk(tab, frame, frame_bytes, range_end_bit, L, c, s, bad)) {
+        fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
+        if (bad) atomicExch(&work->flags[1], 1ull);
+    } else {
+        L.chunkE2[c] = CHUNK_DIRTY;
+        atomicExch(&work->flags[3], 1ull);
+    }
 }
 
-// streams that do not synchronise within a whole chunk: carry the true start forward serially
+// The safety net (dec_verify_kernel found a group that does not start where the one before it ends): one thread
+// carries the true start forward chunk by chunk.  Correct for any stream; slow; not seen on real data.
 __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                        unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
                                        DecWork *work, unsigned long long nch, unsigned long long c0,
@@ -707,29 +832,40 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
     if (work->flags[0] == 0 || tab->single_sym) return;
     DecLayout L(work, nch);
     uint32_t bad = 0;
-    for (unsigned long long c = c0; c < c1; c++) {          // c0 >= 1
-        if (L.chunkE2[c - 1] == 0xFFFFFFFFu) continue;      // predecessor's overflow is what dec_fix2_kernel used
-        const uint32_t s = L.chunkE2[c - 1];
+    for (unsigned long long c = c0 ? c0 : 1; c < c1; c++) {
+        const uint32_t s = L.chunkE[c - 1];
         if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
         fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
+    work->flags[0] = 0;                                 // settled (the next slice starts clean)
 }
 
 // chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
-int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
-                const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                unsigned long long c1)
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+                unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
+                unsigned long long c0, unsigned long long c1, bool speculative)
 {
-    if (c0 == 0) c0 = 1;
     if (c1 <= c0) return HF_OK;
-    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((c1 - c0 + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
+    const unsigned long long g_first = c0 / GROUP_CHUNKS, g_last = (c1 + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
+    if (g_last <= (g_first ? g_first : 1)) return HF_OK;
+    const unsigned long long ng = g_last - (g_first ? g_first : 1);
+    HF_CUDA(c, cudaMemsetAsync(&work->flags[3], 0, 8, c->stream));
+    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, g_first, g_last);
+    HF_LAUNCH_CHECK(c);
+    unsigned long long grid = (ng + S3_TEAMS - 1) / S3_TEAMS;
+    if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
+    HF_PROF(c, "dec_regroup_kernel");
+    dec_regroup_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dec_verify_kernel"); dec_verify_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, c->stream>>>(d_tab, work, nch, g_first, g_last);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
 // -------------------------------------------------------------------------------------------------
 // chunks [c0, c1), c0 a multiple of GROUP_CHUNKS; tail_only ignores the range
 int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
@@ -739,6 +875,7 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
     static bool attr = false;
     if (!attr) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         attr = true;
     }
     unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;

@@ -42,8 +42,10 @@ constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits =
 
 struct DecWork {
     unsigned long long result[4];       // [1] overflow of the last code word past the range end, [2] symbols in the range
-    unsigned long long flags[4];        // [0] any chunk failed to sync, [1] invalid code met, [2] table error
-    // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32, chunkE2[nch] u32 (0xFFFFFFFF = unchanged),
+    unsigned long long flags[4];        // [0] a group does not start where the one before ends (serial kernel needed),
+                                        // [1] invalid code met, [2] table error, [3] a group was left to dec_regroup_kernel
+    // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32 (overflow past the chunk's end),
+    //              chunkE2[nch] u32 (0xFFFFFFFF, or CHUNK_DIRTY on the first chunk of a group that must be redone),
     //              info[nch * DEC_THREADS] u16
 };
 

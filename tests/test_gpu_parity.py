@@ -423,6 +423,31 @@ def test_encode_units_larger_than_the_staging_window(codec, oracle):
         assert np.array_equal(dec.cpu().numpy().view(np.uint16), data)
 
 
+def test_long_runs_do_not_resynchronise(codec, oracle):
+    # A long run of one byte pair is a periodic bit pattern: a walk that enters it out of phase leaves it out of
+    # phase, so the guessed chains of the decoder's groups never meet the true one inside the run.  Runs from a
+    # few KiB to several MiB (several 32 KiB groups of payload), of symbols with short and with long codes.
+    rng = np.random.default_rng(5)
+    parts = []
+    for k, run in enumerate((3000, 70001, 400000, 1 << 20, 3 << 20, 9 << 20)):
+        parts.append(synth.zipf_bytes(200000 + 2 * k, 1.2, 40 + k))
+        val = (0, 0x20, 0x41, 0xFF, 0x00, 0x0A)[k]
+        parts.append(np.full(run, val, np.uint8))
+    parts.append(rng.integers(0, 256, 100001, dtype=np.uint8))
+    data = np.concatenate(parts)
+    d = dev(data)
+    image = codec.compress(d)
+    assert np.array_equal(image.cpu().numpy(), oracle.compress(data))
+    back = codec.decompress(image)
+    assert torch.equal(back, d)
+    # the same through ranges, as the ranks of a sharded job see it (cuts inside the runs)
+    img = image.cpu().numpy()
+    hdr = (int(codec.parse_header(image)[1].payload_start_bit) + 7) // 8
+    cuts = sorted(int(x) for x in rng.integers(hdr, img.size, 3))
+    got = _decode_by_ranges(codec, img, cuts, True)
+    assert np.array_equal(got, data[: data.size & ~1])
+
+
 def test_round_trip_across_chunk_and_group_boundaries(codec, oracle):
     # payload sizes around the decoder's 16 KiB chunks and 32 KiB groups, and around the 1 KiB spans in them
     base = synth.mixed(1 << 20, seg_bytes=1 << 16)
