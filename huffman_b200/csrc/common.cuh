@@ -124,6 +124,9 @@ struct Ctx {
     void *d_tab;
     void *d_hist;
     void *d_scan;                   // block totals of the decoder's chunk scan (SCAN_BLOCKS_MAX u64)
+    // kernels whose dynamic shared-memory limit has been raised on THIS context's device (a process may hold
+    // contexts on several GPUs; the attribute is per device)
+    bool smem_attr[8];
     bool decode_exact_only;         // hf_set_decode_mode: kept for ABI compatibility, the decoder has one (exact) mode
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
@@ -132,6 +135,7 @@ struct Ctx {
     cudaEvent_t *prof_ev;           // 2 * PROF_CAP events, created on first enable
     const char **prof_name;         // PROF_CAP static strings
 };
+enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE };
 constexpr uint32_t PROF_CAP = 8192;
 constexpr uint32_t PIPE_SLOTS = 4096;
 constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload

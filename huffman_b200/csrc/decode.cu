@@ -428,10 +428,9 @@ int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, Deco
     int rc = ensure_ws(c, sizeof(TabSrc));
     if (rc) return rc;
     TabSrc *src = reinterpret_cast<TabSrc *>(c->ws);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->smem_attr[ATTR_PARSE]) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HDR_STAGE + 32));
-        attr_set = true;
+        c->smem_attr[ATTR_PARSE] = true;
     }
     // status of an earlier use must not leak into this parse
     HF_CUDA(c, cudaMemsetAsync(&d_tab->status, 0, sizeof(uint32_t), c->stream));

@@ -368,11 +368,12 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
     // is periodic: a walk that enters it out of phase leaves it out of phase) makes the fix-point hand a lane
     // the same few starts again and again; a remembered start costs no walk, and the record of the final start
     // is rebuilt once at the end.
-    uint32_t rec_p = p, rec_end = 0, mslot = 0;
+    uint32_t rec_p = p, rec_end = 0, mslot = 0, nwalk = 0;
     unsigned long long memo = 0;
     auto memo_add = [&](uint32_t st, uint32_t en) {
         memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((st + 1) << 8) | en) << (16 * mslot));
         mslot = (mslot + 1) & 3;
+        nwalk++;
     };
     if (lim) {
         if (p < lim) { walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
@@ -392,10 +393,12 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
             if (!__any_sync(0xFFFFFFFFu, need)) break;
             if (need) {
                 uint32_t hit = 0;                   // ((q + 1) << 8) | end of a walk from q done before
+                if (nwalk >= 2) {                   // the first correction of a guess cannot be a repeat
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
-                    if ((en >> 8) == q + 1) hit = en;
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
+                        if ((en >> 8) == q + 1) hit = en;
+                    }
                 }
                 if (hit) {
                     end = hit & 0xFFu;              // rec stays with the walk it describes
@@ -872,11 +875,10 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
                  unsigned long long c0, unsigned long long c1, bool tail_only)
 {
-    static bool attr = false;
-    if (!attr) {
+    if (!c->smem_attr[ATTR_SYNC]) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         HF_CUDA(c, cudaFuncSetAttribute(dec_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
-        attr = true;
+        c->smem_attr[ATTR_SYNC] = true;
     }
     unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
     // tail_only: the overflow past the range end, speculatively from a guessed start up to eight groups
@@ -902,10 +904,9 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
                   unsigned long long c1, unsigned long long n_symbols, uint16_t *out)
 {
     if (c1 <= c0) return HF_OK;
-    static bool attr = false;
-    if (!attr) {
+    if (!c->smem_attr[ATTR_WRITE]) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
-        attr = true;
+        c->smem_attr[ATTR_WRITE] = true;
     }
     unsigned long long grid = ((c1 - c0) * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;

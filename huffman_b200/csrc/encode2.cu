@@ -528,11 +528,10 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     W.group_start = reinterpret_cast<unsigned long long *>(p); p += b_gstart;
     W.block_start = reinterpret_cast<unsigned long long *>(p);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->smem_attr[ATTR_ENCODE]) {
         HF_CUDA(c, cudaFuncSetAttribute(encode2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM));
         HF_CUDA(c, cudaFuncSetAttribute(enc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSYM));
-        attr_set = true;
+        c->smem_attr[ATTR_ENCODE] = true;
     }
     // start_bit may exceed 8: fold whole bytes into the pointer
     d_stream += start_bit >> 3;

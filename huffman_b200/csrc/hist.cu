@@ -162,11 +162,10 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
         size_t part_bytes = (size_t)grid * HIST_WORDS * sizeof(uint32_t);
         int rc = ensure_ws(c, part_bytes);
         if (rc) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!c->smem_attr[ATTR_HIST]) {
             HF_CUDA(c, cudaFuncSetAttribute(hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             HIST_WORDS * 4));
-            attr_set = true;
+            c->smem_attr[ATTR_HIST] = true;
         }
         HF_PROF(c, "hist_smem_kernel"); hist_smem_kernel<<<grid, HIST_THREADS, HIST_WORDS * 4, c->stream>>>(
             reinterpret_cast<const uint4 *>(p + head), n_vec, (uint32_t *)c->ws, d_hist);
