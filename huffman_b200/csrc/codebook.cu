@@ -317,16 +317,31 @@ cb_entry_scan_kernel(const CbWork *__restrict__ w, uint32_t *__restrict__ entry_
 {
     __shared__ uint32_t s_scan[40];
     const uint32_t U = w->U, tid = threadIdx.x;
-    const uint32_t per = NSYM / CB_THREADS;
+    constexpr uint32_t per = NSYM / CB_THREADS;     // 64 consecutive entries per thread, as 16 independent 128-bit loads
+    uint4 v[per / 4];
+    const uint4 *src = reinterpret_cast<const uint4 *>(w->entry_bits + tid * per);
     uint32_t sum = 0;
-    for (uint32_t j = 0; j < per; j++) {
-        uint32_t k = tid * per + j;
-        sum += k < U ? w->entry_bits[k] : 0;
+#pragma unroll
+    for (uint32_t j = 0; j < per / 4; j++) {
+        const uint32_t k = tid * per + 4 * j;
+        uint4 x = k < U ? src[j] : make_uint4(0, 0, 0, 0);          // entries past U hold stale values
+        if (k + 1 >= U) x.y = 0;
+        if (k + 2 >= U) x.z = 0;
+        if (k + 3 >= U) x.w = 0;
+        v[j] = x;
+        sum += x.x + x.y + x.z + x.w;
     }
     uint32_t run = block_excl_scan_u32(sum, s_scan, nullptr);
-    for (uint32_t j = 0; j < per; j++) {
-        uint32_t k = tid * per + j;
-        if (k < U) { entry_off[k] = run; run += w->entry_bits[k]; }
+    uint4 *dst = reinterpret_cast<uint4 *>(entry_off + tid * per);
+#pragma unroll
+    for (uint32_t j = 0; j < per / 4; j++) {
+        const uint32_t k = tid * per + 4 * j;
+        uint4 o;
+        o.x = run; run += v[j].x;
+        o.y = run; run += v[j].y;
+        o.z = run; run += v[j].z;
+        o.w = run; run += v[j].w;
+        if (k < U) dst[j] = o;                                      // offsets past U are never read
     }
 }
 
