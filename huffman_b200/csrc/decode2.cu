@@ -96,17 +96,22 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
     }
 }
 
-// bases of the micro trees (exclusive scan of their leaf counts in prefix order) and the leaf symbols
+// bases of the micro trees: exclusive scan of their leaf counts in prefix order (one CTA, 16 prefixes per thread)
 __global__ void __launch_bounds__(1024, 1)
 dt_micro_kernel(DecodeTable *__restrict__ tab)
 {
     __shared__ uint32_t s_w[33];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr uint32_t PER = (1u << MICRO_K) / 1024;    // 16 prefixes per thread
+    uint4 v[PER / 4];
+    uint4 *ent = reinterpret_cast<uint4 *>(tab->t14 + tid * PER);
     uint32_t sum = 0;
-    for (uint32_t j = 0; j < PER; j++) {
-        const uint32_t e = tab->t14[tid * PER + j];
-        if (e & 1u) sum += __popc(e & 0xFFFFu);
+#pragma unroll
+    for (uint32_t j = 0; j < PER / 4; j++) {
+        v[j] = ent[j];
+        const uint32_t e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (e4[k] & 1u) sum += __popc(e4[k] & 0xFFFFu);
     }
     uint32_t x = sum;
 #pragma unroll
@@ -114,24 +119,38 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
     if (lane == 31) s_w[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        const uint32_t v = s_w[lane];
-        uint32_t t = v;
+        const uint32_t t0 = s_w[lane];
+        uint32_t t = t0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
-        s_w[lane] = t - v;
+        s_w[lane] = t - t0;
     }
     __syncthreads();
     uint32_t base = x - sum + s_w[wid];
-    for (uint32_t j = 0; j < PER; j++) {
-        const uint32_t p = tid * PER + j;
-        const uint32_t e = tab->t14[p];
-        if (!(e & 1u)) continue;
-        const uint32_t mask = e & 0xFFFFu;
-        if (base + __popc(mask) > NSYM) { tab->t14[p] = 0; continue; }     // cannot happen for a prefix code
-        tab->t14[p] = (base << 16) | mask;
-        for (uint32_t m = mask; m; m &= m - 1)
-            tab->leaves[base++] = tab->micro_sym[p * (1u << MICRO_D) + (__ffs(m) - 1)];
+#pragma unroll
+    for (uint32_t j = 0; j < PER / 4; j++) {
+        uint32_t e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(e4[k] & 1u)) continue;
+            const uint32_t mask = e4[k] & 0xFFFFu, n = __popc(mask);
+            e4[k] = base + n > NSYM ? 0u : ((base << 16) | mask);       // cannot overflow for a prefix code
+            base += n;
+        }
+        ent[j] = make_uint4(e4[0], e4[1], e4[2], e4[3]);
     }
+}
+
+// the leaf symbols of every micro tree, in slot order
+__global__ void dt_leaves_kernel(DecodeTable *__restrict__ tab)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (1u << MICRO_K)) return;
+    const uint32_t e = tab->t14[p];
+    if (!(e & 1u)) return;
+    uint32_t base = e >> 16;
+    for (uint32_t m = e & 0xFFFFu; m; m &= m - 1)
+        tab->leaves[base++] = tab->micro_sym[p * (1u << MICRO_D) + (__ffs(m) - 1)];
 }
 
 int launch_table_planes(Ctx *c, DecodeTable *d_tab)
@@ -139,6 +158,8 @@ int launch_table_planes(Ctx *c, DecodeTable *d_tab)
     HF_PROF(c, "dt_planes_kernel"); dt_planes_kernel<<<(1u << FLAT_MAX) / 256, 256, 0, c->stream>>>(d_tab);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dt_micro_kernel"); dt_micro_kernel<<<1, 1024, 0, c->stream>>>(d_tab);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dt_leaves_kernel"); dt_leaves_kernel<<<(1u << MICRO_K) / 256, 256, 0, c->stream>>>(d_tab);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
