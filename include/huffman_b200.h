@@ -136,8 +136,8 @@ int hf_shard_payload_bits(hf_ctx *ctx, const uint64_t *d_shard_hist, const void 
 int hf_header_pack(hf_ctx *ctx, const void *d_codebook, uint64_t n_bytes, uint32_t last_byte,
                    uint8_t *d_file, uint64_t capacity);
 
-/* C:50-74 + C:541-588 + C:597-601 (populateCWLength, scan, encodeFromCW, tail flush)
- * as one single-pass kernel.  Writes the code words of the byte pairs of
+/* C:50-74 + C:541-588 + C:597-601 (populateCWLength, scan, encodeFromCW, tail flush):
+ * bits per 512-symbol unit, a two-level scan, one warp-independent packing kernel.  Writes the code words of the byte pairs of
  * d_in[0 .. n_bytes & ~1) as one MSB-first bit stream starting `start_bit` bits after
  * d_stream.  Bits of the first byte before the start phase are preserved (they belong to
  * the header or to the previous shard); the final partial byte is zero padded. */
@@ -170,13 +170,12 @@ int hf_decode(hf_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint6
  * the range; halo_bytes (>= 16) after it are readable: the following bytes of the same stream,
  * zeros past its end.
  *   hf_range_overflow: where does the first code word AFTER the range start?  Found speculatively
- *     by self-synchronising over the last 16 KiB of the range; d_result[1] = bits past the range
- *     end.  The ranks all-gather these values: each is the next rank's first bit.
+ *     by self-synchronising over the last 256 KiB of the range from a guessed start; d_result[1] =
+ *     bits past the range end.  The ranks all-gather these values: each is the next rank's first bit.
  *   hf_decode_range: decodes the code words that start inside the range, the first one first_bit
  *     bits into it, into d_out (at most out_symbols).  d_result (device u64[4]): [1] overflow of
  *     the last code word past the range end (must equal what hf_range_overflow predicted),
- *     [2] symbols decoded, [3] flags: 1 the stream did not self-synchronise within a 16 KiB
- *     chunk, 4 invalid code, 8 out_symbols too small, 16 internal.  Any flag means d_out must not
+ *     [2] symbols decoded, [3] flags: 4 invalid code, 8 out_symbols too small.  Any flag means d_out must not
  *     be used.  Both calls are asynchronous. */
 int hf_range_overflow(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
                       const void *d_decode_table, uint64_t *d_result);
@@ -184,9 +183,8 @@ int hf_decode_range(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, u
                     uint64_t first_bit, const void *d_decode_table, uint8_t *d_out, uint64_t out_symbols,
                     uint64_t *d_result);
 
-/* hf_decode / hf_decompress normally run the single-pass decoder and fall back (on the device) to
- * the exact multi-pass kernels for streams that do not self-synchronise; exact_only = 1 forces the
- * exact kernels (used by the tests to cover both). */
+/* Kept for ABI compatibility: the decoder has ONE mode, exact self-synchronising decode (an earlier revision also had a
+ * speculative single-pass decoder that this switch turned off).  The argument is stored and ignored. */
 int hf_set_decode_mode(hf_ctx *ctx, int exact_only);
 
 /* whole `extract` data path on device buffers.  Synchronises. */
