@@ -340,6 +340,34 @@ def run_ours(args):
     for p in phases.values():
         p["frac"] = p["gbs_alg"] / (hbm_peak * world)
 
+    # ---- the same step with the optional side index: the compressor also writes one u16 record per
+    #      256 bits of payload and the decoder skips its synchronisation pass; reported beside the headline, not in it
+    indexed = None
+    if job is None and not args.no_index:
+        index_buf = torch.empty(int(codec.lib.hf_index_bound(n_shard)), dtype=torch.uint8, device=dev)
+        img_i, idx_i = codec.compress_indexed(chunk, out_img, index_buf)
+        back_i = codec.decompress_indexed(img_i, idx_i, out_dec)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(back_i[:n_shard], chunk)), "indexed round trip failed"
+        evi = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+        codec.profile(True)
+        evi[0].record()
+        for i in range(args.steps):
+            img_i, idx_i = codec.compress_indexed(chunk, out_img, index_buf)
+            evi[2 * i + 1].record()
+            codec.decompress_indexed(img_i, idx_i, out_dec)
+            evi[2 * i + 2].record()
+        torch.cuda.synchronize()
+        prof_i = codec.profile_read()
+        codec.profile(False)
+        ti_enc = sum(evi[2 * i].elapsed_time(evi[2 * i + 1]) for i in range(args.steps))
+        ti_dec = sum(evi[2 * i + 1].elapsed_time(evi[2 * i + 2]) for i in range(args.steps))
+        indexed = {"value": 2 * n_total * k / ((ti_enc + ti_dec) * 1e-3) / 1e9, "unit": UNIT,
+                   "encode_gbs": n_total * k / (ti_enc * 1e-3) / 1e9, "decode_gbs": n_total * k / (ti_dec * 1e-3) / 1e9,
+                   "index_bytes": int(idx_i.numel()), "synchronisation_pass_skipped": "dec_sync3_kernel" not in prof_i,
+                   "enc_index_kernel_ms": prof_i.get("enc_index_kernel", (1, 0.0))[1] / max(prof_i.get("enc_index_kernel", (1, 0.0))[0], 1)}
+        del index_buf
+
     # ---- end to end through the host-buffer C-ABI calls (pinned host memory, copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -365,7 +393,7 @@ def run_ours(args):
                        "sharding": f"contiguous chunks x{world}", "l2": "inputs >> 126 MB L2, no flush needed",
                        "step": "full compress then full decompress of the stream"},
             "encode_gbs": enc_gbs, "decode_gbs": dec_gbs, "phases": phases,
-            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "with_side_index": indexed,
             "gpu_launches": launches, "clocks": clocks,
             "collectives_per_step": (job.collectives // (k + args.warmup + 0)) if job else 0,
         }
@@ -454,6 +482,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-index", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -75,6 +75,9 @@ _SIGS = {
     "hf_decode_range": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P, _U64, _P]),
     "hf_set_decode_mode": (ctypes.c_int, [_P, ctypes.c_int]),
     "hf_decompress": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_index_bound": (_U64, [_U64]),
+    "hf_compress_indexed": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64), _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_decompress_indexed": (ctypes.c_int, [_P, _P, _U64, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_compress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_decompressed_size_host": (ctypes.c_int, [_P, _U64, ctypes.POINTER(_U64)]),
     "hf_decompress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),

@@ -129,6 +129,29 @@ class Codec:
         self._check(self.lib.hf_compress(self.ctx, _ptr(data), n, _ptr(out), out.numel(), ctypes.byref(size)))
         return out[: size.value]
 
+    def compress_indexed(self, data, out=None, index=None):
+        """like compress, plus the optional side index (a uint8 CUDA tensor) that lets decompress_indexed skip the
+        synchronisation pass; the image is the same bytes"""
+        n = data.numel()
+        if out is None:
+            out = torch.empty(self.compress_bound(n), dtype=torch.uint8, device=self.device)
+        if index is None:
+            index = torch.empty(int(self.lib.hf_index_bound(n)), dtype=torch.uint8, device=self.device)
+        size, isize = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self._check(self.lib.hf_compress_indexed(self.ctx, _ptr(data), n, _ptr(out), out.numel(), ctypes.byref(size),
+                                                 _ptr(index), index.numel(), ctypes.byref(isize)))
+        return out[: size.value], index[: isize.value]
+
+    def decompress_indexed(self, image, index, out=None):
+        """decompress with a side index; an index that is empty, stale or wrong is ignored (self-synchronising decode)"""
+        size = ctypes.c_uint64(0)
+        if out is None:
+            _, info = self.parse_header(image)
+            out = torch.empty(max(int(info.original_bytes), 1), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.hf_decompress_indexed(self.ctx, _ptr(image), image.numel(), _ptr(index), index.numel(),
+                                                   _ptr(out), out.numel(), ctypes.byref(size)))
+        return out[: size.value]
+
     # ---- decompress stages ----
     def parse_header(self, image, table=None):
         if table is None:

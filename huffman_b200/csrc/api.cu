@@ -314,10 +314,22 @@ int hf_encode(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, const void *d_
     return launch_encode(CTX(ctx), d_in, n_bytes, reinterpret_cast<const Codebook *>(d_codebook), d_stream, start_bit, 0);
 }
 
-// shared tail of hf_compress / hf_compress_host: codebook -> sizes -> header -> payload.
+// the side index object: this header, then n_subs u16 records (encode2.cu enc_index_kernel)
+struct IndexHeader {
+    uint32_t magic, version;            // "HFIX", 1
+    uint32_t align16;                   // address of the image modulo 16 the records were made for
+    uint32_t reserved;
+    unsigned long long payload_start_bit, n_subs, file_bytes, original_bytes;
+    unsigned long long pad[2];
+};
+static_assert(sizeof(IndexHeader) == 64, "index header is 64 bytes");
+static const uint32_t INDEX_MAGIC = 0x58494648u;
+
+// shared tail of hf_compress / hf_compress_host: codebook -> sizes -> header -> payload [-> side index].
 // *h_last is read after the synchronisation inside hf_codebook_info.
 static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *h_last, uint8_t *d_file,
-                               uint64_t capacity, uint64_t *h_file_bytes)
+                               uint64_t capacity, uint64_t *h_file_bytes, uint8_t *d_index = nullptr,
+                               uint64_t index_capacity = 0, uint64_t *h_index_bytes = nullptr)
 {
     hf_ctx *ctx = reinterpret_cast<hf_ctx *>(c);
     Codebook *cb = reinterpret_cast<Codebook *>(c->d_cb);
@@ -335,8 +347,29 @@ static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const ui
                        (unsigned long long)capacity);
     rc = hf_header_pack(ctx, cb, n, (n & 1) ? *h_last : 0, d_file, capacity);
     if (rc) return rc;
-    return launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64,
-                         info.max_code_bits ? info.max_code_bits : 1);
+    rc = launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64,
+                       info.max_code_bits ? info.max_code_bits : 1);
+    if (rc || !d_index) return rc;
+    // the side index: records for exactly the stream just packed, at this image's alignment
+    if (h_index_bytes) *h_index_bytes = 0;
+    if (info.max_code_bits == 0 || n < 2) return HF_OK;             // no payload: nothing to index
+    const uint8_t *d_stream = d_file + preamble_bytes(n);
+    const uint64_t stream_bytes = total - preamble_bytes(n), start_bit = info.table_bits + 64;
+    const uint64_t n_subs = index_subs(d_stream, stream_bytes, start_bit);
+    const uint64_t need = sizeof(IndexHeader) + 2 * n_subs;
+    if (need > index_capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_compress_indexed: index needs %llu bytes, capacity %llu",
+                       (unsigned long long)need, (unsigned long long)index_capacity);
+    if ((uintptr_t)d_index & 15) return set_err(c, HF_ERR_ARG, "hf_compress_indexed: index buffer must be 16-byte aligned");
+    rc = launch_encode_index(c, d_in, n, cb, d_stream, start_bit, reinterpret_cast<uint16_t *>(d_index + sizeof(IndexHeader)), n_subs);
+    if (rc) return rc;
+    IndexHeader *h = reinterpret_cast<IndexHeader *>((uint8_t *)c->h_scratch + 3584);
+    memset(h, 0, sizeof(*h));
+    h->magic = INDEX_MAGIC; h->version = 1; h->align16 = (uint32_t)((uintptr_t)d_file & 15);
+    h->payload_start_bit = preamble_bytes(n) * 8ull + start_bit; h->n_subs = n_subs; h->file_bytes = total; h->original_bytes = n;
+    HF_CUDA(c, cudaMemcpyAsync(d_index, h, sizeof(*h), cudaMemcpyHostToDevice, c->stream));
+    if (h_index_bytes) *h_index_bytes = need;
+    return HF_OK;
 }
 
 int hf_compress(hf_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_file, uint64_t capacity,
@@ -352,6 +385,31 @@ int hf_compress(hf_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_file, u
     *h_last = 0;
     if (n & 1) HF_CUDA(c, cudaMemcpyAsync(h_last, d_in + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
     rc = compress_after_hist(c, d_in, n, h_last, d_file, capacity, h_file_bytes);
+    if (rc) return rc;
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+uint64_t hf_index_bound(uint64_t n)
+{   // records for the largest image n bytes can give, at any alignment
+    const uint64_t frame = hf_compress_bound(n) + 16;
+    const uint64_t nch = (frame * 8 + 131071) / 131072 + 1;
+    return sizeof(IndexHeader) + 2 * nch * 512;
+}
+
+int hf_compress_indexed(hf_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_file, uint64_t capacity,
+                        uint64_t *h_file_bytes, uint8_t *d_index, uint64_t index_capacity, uint64_t *h_index_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if ((!d_in && n) || !d_file || !d_index) return set_err(c, HF_ERR_ARG, "hf_compress_indexed: null pointer");
+    HF_CUDA(c, cudaMemsetAsync(c->d_hist, 0, NSYM * 8, c->stream));
+    int rc = launch_histogram(c, d_in, n, reinterpret_cast<unsigned long long *>(c->d_hist));
+    if (rc) return rc;
+    uint8_t *h_last = reinterpret_cast<uint8_t *>(c->h_scratch) + 2048;
+    *h_last = 0;
+    if (n & 1) HF_CUDA(c, cudaMemcpyAsync(h_last, d_in + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    rc = compress_after_hist(c, d_in, n, h_last, d_file, capacity, h_file_bytes, d_index, index_capacity, h_index_bytes);
     if (rc) return rc;
     HF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HF_OK;
@@ -457,6 +515,48 @@ int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8
     }
     if (info.is_odd) HF_CUDA(c, cudaMemsetAsync(d_out + info.original_bytes - 1, (int)info.last_byte, 1, c->stream));   // D:286-289
     if (nsym) return check_decode_flags(c);
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HF_OK;
+}
+
+int hf_decompress_indexed(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, const uint8_t *d_index,
+                          uint64_t index_bytes, uint8_t *d_out, uint64_t capacity, uint64_t *h_out_bytes)
+{
+    NEED_CTX(ctx);
+    Ctx *c = CTX(ctx);
+    if (!d_index || index_bytes < sizeof(IndexHeader)) return hf_decompress(ctx, d_file, file_bytes, d_out, capacity, h_out_bytes);
+    hf_header_info_t info;
+    int rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);
+    if (rc) return rc;
+    if (h_out_bytes) *h_out_bytes = info.original_bytes;
+    if (info.original_bytes > capacity)
+        return set_err(c, HF_ERR_CAPACITY, "hf_decompress_indexed: need %llu bytes, capacity %llu",
+                       (unsigned long long)info.original_bytes, (unsigned long long)capacity);
+    if (info.original_bytes && !d_out) return set_err(c, HF_ERR_ARG, "hf_decompress_indexed: null output");
+    const uint64_t nsym = info.original_bytes / 2;
+    IndexHeader *h = reinterpret_cast<IndexHeader *>((uint8_t *)c->h_scratch + 3584);
+    HF_CUDA(c, cudaMemcpyAsync(h, d_index, sizeof(*h), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    DecodeTable *tab = reinterpret_cast<DecodeTable *>(c->d_tab);
+    // the index must be the one of THIS image at THIS alignment; anything else decodes without it
+    bool usable = nsym != 0 && info.max_code_bits != 0 && h->magic == INDEX_MAGIC && h->version == 1 &&
+                  h->align16 == (uint32_t)((uintptr_t)d_file & 15) && h->payload_start_bit == info.payload_start_bit &&
+                  h->file_bytes == file_bytes && h->original_bytes == info.original_bytes &&
+                  ((uintptr_t)d_index & 15) == 0 && index_bytes >= sizeof(IndexHeader) + 2 * h->n_subs &&
+                  h->n_subs == index_subs(d_file, file_bytes, info.payload_start_bit);
+    if (usable) {
+        rc = launch_decode_indexed(c, d_file, file_bytes, info.payload_start_bit, nsym, tab, d_out,
+                                   reinterpret_cast<const uint16_t *>(d_index + sizeof(IndexHeader)), h->n_subs);
+        if (rc == HF_OK) rc = check_decode_flags(c);
+        usable = rc == HF_OK;                           // a record that does not match the walk: decode again without
+    }
+    if (!usable && nsym) {
+        rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, tab, d_out);
+        if (rc) return rc;
+        rc = check_decode_flags(c);
+        if (rc) return rc;
+    }
+    if (info.is_odd) HF_CUDA(c, cudaMemsetAsync(d_out + info.original_bytes - 1, (int)info.last_byte, 1, c->stream));   // D:286-289
     HF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HF_OK;
 }

@@ -135,7 +135,7 @@ struct Ctx {
     cudaEvent_t *prof_ev;           // 2 * PROF_CAP events, created on first enable
     const char **prof_name;         // PROF_CAP static strings
 };
-enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE };
+enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE, ATTR_INDEX };
 constexpr uint32_t PROF_CAP = 8192;
 constexpr uint32_t PIPE_SLOTS = 4096;
 constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload
@@ -175,6 +175,8 @@ int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t 
                        uint8_t *d_file, uint64_t capacity);
 int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb,
                   uint8_t *d_stream, uint64_t start_bit, uint32_t maxlen_hint);
+int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, const uint8_t *d_stream,
+                        uint64_t start_bit, uint16_t *d_rec, uint64_t n_subs);
 int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, DecodeTable *d_tab,
                         hf_header_info_t *d_info);
 int launch_table_from_codebook(Ctx *c, const Codebook *d_cb, DecodeTable *d_tab);
@@ -192,6 +194,9 @@ struct DecodeJob {
 int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
                  const DecodeTable *d_tab, uint8_t *d_out, DecodeJob *job);
 int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned long long c1);
+int launch_decode_indexed(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
+                          const DecodeTable *d_tab, uint8_t *d_out, const uint16_t *d_rec, uint64_t n_subs);
+uint64_t index_subs(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit);
 int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, uint64_t first_bit,
                         bool tail_only, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
                         unsigned long long *d_result);

@@ -392,7 +392,9 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
                  unsigned long long c0, unsigned long long c1, bool tail_only);
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out);
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, bool check);
+int launch_idx_chunks(Ctx *c, DecWork *work, unsigned long long nch);
+int launch_idx_total(Ctx *c, DecWork *work, unsigned long long n_symbols);
 
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
@@ -470,7 +472,7 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
     if (rc) return rc;
     rc = launch_scan(c, work, nch, c0, c1);
     if (rc) return rc;
-    return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16);
+    return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16, false);
 }
 
 // A decode of one stream, all at once (launch_decode) or in slices of chunks as its bytes arrive from the host
@@ -510,6 +512,40 @@ int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned l
 {
     return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, job.n_symbols, job.tab, job.out16,
                                reinterpret_cast<DecWork *>(job.work), job.nch, c0, c1);
+}
+
+// Decode with the records of a side index (n_subs u16, as the compressor's enc_index_kernel wrote them for this
+// stream at this alignment) in place of the synchronisation kernels.  The write kernel checks every record against
+// the walk it drives (flags[1] on a mismatch: the caller decodes again without the index).
+int launch_decode_indexed(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
+                          const DecodeTable *d_tab, uint8_t *d_out, const uint16_t *d_rec, uint64_t n_subs)
+{
+    if (n_symbols == 0) return HF_OK;
+    DecodeJob job;
+    int rc = decode_begin(c, d_stream, stream_bytes, start_bit, n_symbols, d_tab, d_out, &job);
+    if (rc) return rc;
+    if (n_subs != job.nch * DEC_THREADS) return set_err(c, HF_ERR_FORMAT, "index does not fit the stream");
+    DecWork *work = reinterpret_cast<DecWork *>(job.work);
+    DecLayout L(work, job.nch);
+    HF_CUDA(c, cudaMemcpyAsync(L.info, d_rec, n_subs * 2, cudaMemcpyDeviceToDevice, c->stream));
+    rc = launch_idx_chunks(c, work, job.nch);
+    if (rc) return rc;
+    rc = launch_scan(c, work, job.nch, 0, job.nch);
+    if (rc) return rc;
+    rc = launch_idx_total(c, work, n_symbols);
+    if (rc) return rc;
+    return launch_write2(c, job.frame, job.frame_bytes, job.F0, d_tab, work, job.nch, 0, job.nch, n_symbols, job.out16, true);
+}
+
+// number of index records of a stream of stream_bytes bytes whose first code word sits start_bit bits after d_stream
+uint64_t index_subs(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit)
+{
+    d_stream += start_bit >> 3;
+    stream_bytes -= start_bit >> 3;
+    const unsigned long long frame_bytes = ((uintptr_t)d_stream & 15) + stream_bytes;
+    unsigned long long nch = (frame_bytes * 8 + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (nch == 0) nch = 1;
+    return nch * DEC_THREADS;
 }
 
 int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit,

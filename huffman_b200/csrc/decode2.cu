@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                   unsigned long long c0, unsigned long long c1, unsigned long long n_symbols,
-                  uint16_t *__restrict__ out)
+                  uint16_t *__restrict__ out, uint32_t check)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
@@ -708,8 +708,66 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             }
             __syncwarp();
         }
+        if (check) {
+            // records that did not come from the synchronisation kernels (a side index): a walk of `cnt` code words
+            // must end exactly where the next subsequence says its first code word starts
+            uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, inf, 1);
+            if (lane == 31) {
+                const unsigned long long ns = c * DEC_THREADS + t + 1;
+                nxt = ns < nch * DEC_THREADS ? (uint32_t)L.info[ns] : 0u;
+            }
+            const bool last = base + off + cnt == n_symbols;        // my last code word is the stream's last: no successor
+            if (cnt && my_end == off + cnt && !last && ((nxt >> 6) == 0 || pos < SUB_BITS || pos - SUB_BITS != (nxt & 63u))) bad = 1;
+        }
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// chunk totals of records that came from a side index; a count no subsequence can have marks the index invalid
+__global__ void idx_chunks_kernel(DecWork *work, unsigned long long nch)
+{
+    const unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= nch) return;
+    const uint32_t lane = threadIdx.x & 31;
+    DecLayout L(work, nch);
+    const uint4 *ip = reinterpret_cast<const uint4 *>(L.info + c * DEC_THREADS);
+    const uint4 a = ip[2 * lane], d = ip[2 * lane + 1];
+    const uint32_t w8[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    uint32_t sum = 0, worst = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t lo = (w8[i] & 0xFFFFu) >> 6, hi = w8[i] >> 22;
+        sum += lo + hi;
+        worst = max(worst, max(lo, hi));
+    }
+    sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+    worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+    if (lane == 0) {
+        L.chunkCnt[c] = sum;
+        L.chunkE[c] = 0;
+        L.chunkE2[c] = 0xFFFFFFFFu;
+        if (worst > SUB_BITS) atomicExch(&work->flags[1], 1ull);
+    }
+}
+
+// the records of a side index must account for every symbol of the stream, no more, no fewer
+__global__ void idx_total_kernel(DecWork *work, unsigned long long n_symbols)
+{
+    if (work->result[2] != n_symbols) atomicExch(&work->flags[1], 1ull);
+}
+
+int launch_idx_total(Ctx *c, DecWork *work, unsigned long long n_symbols)
+{
+    HF_PROF(c, "idx_total_kernel"); idx_total_kernel<<<1, 1, 0, c->stream>>>(work, n_symbols);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+int launch_idx_chunks(Ctx *c, DecWork *work, unsigned long long nch)
+{
+    HF_PROF(c, "idx_chunks_kernel"); idx_chunks_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, c->stream>>>(work, nch);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -922,7 +980,7 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
 
 int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out)
+                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, bool check)
 {
     if (c1 <= c0) return HF_OK;
     if (!c->smem_attr[ATTR_WRITE]) {
@@ -932,7 +990,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     unsigned long long grid = ((c1 - c0) * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -502,18 +502,139 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
     }
 }
 
-int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
-                  uint64_t start_bit, uint32_t maxlen_hint)
+// ---------------------------------------------------------------------------------------------
+// Side index: the format has no offset array, so the decoder normally finds the code word
+// boundaries by self-synchronisation.  For streams WE write, the compressor can hand the decoder what its
+// synchronisation kernels would compute: one u16 record per 256-bit subsequence of the payload frame,
+// (offset of the first code word boundary at or after the subsequence start) | (code words starting in it) << 6.
+// A unit writes the records of the subsequences that end inside it with plain stores and adds its share of the two
+// it shares with its neighbours with one atomic each (the records are zeroed first).  Reads N, writes C / 16.
+constexpr uint32_t IDX_SUB_BITS = 256;                              // = SUB_BITS of the decoder
+constexpr uint32_t IDX_SUBS_MAX = 160;                              // a unit spans <= 512 * 64 / 256 + 2 subsequences
+
+__global__ void __launch_bounds__(BITS_THREADS)
+enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, Enc2Work W,
+                 uint64_t ngroups, unsigned long long bit0, uint16_t *__restrict__ rec, unsigned long long n_subs)
 {
-    (void)maxlen_hint;
-    const uint64_t n_sym = n_bytes / 2;
-    if (n_sym == 0) return HF_OK;
-    if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
-    if ((uintptr_t)d_cb & 15) return set_err(c, HF_ERR_ARG, "hf_encode: codebook must be 16-byte aligned");
+    extern __shared__ __align__(16) uint8_t s_len[];               // lenf plane, 64 KiB
+    __shared__ uint32_t s_acc[BITS_THREADS / 32][IDX_SUBS_MAX];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cb->lenf);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_len);
+        for (uint32_t i = tid; i < NSYM / 16; i += BITS_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
+    uint32_t *acc = s_acc[wid];
+    const uint64_t warp0 = (uint64_t)blockIdx.x * (BITS_THREADS / 32) + wid;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (BITS_THREADS / 32);
+    for (uint64_t g = warp0; g < ngroups; g += nwarps) {
+        const unsigned long long gstart = bit0 + W.block_start[g / SCAN_PER_BLOCK] + W.group_start[g];
+        const uint32_t ub = W.unit_bits[g * GROUP_UNITS + lane];
+        uint32_t ux = ub;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ux, o); if (lane >= o) ux += y; }
+        ux -= ub;
+        uint32_t carry_len = 0;                                     // length of the last code word of the unit before
+        uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0;              // the next unit's symbols, loaded one unit ahead
+        bool have_nx = false;
+        for (uint32_t u = 0; u < GROUP_UNITS; u++) {
+            const uint64_t unit = g * GROUP_UNITS + u;
+            if (unit * UNIT_SYMS >= n_sym) break;
+            const uint32_t bits = __shfl_sync(0xFFFFFFFFu, ub, u);
+            const unsigned long long S = gstart + __shfl_sync(0xFFFFFFFFu, ux, u);     // frame bit of the unit's first code word
+            uint32_t len[16];
+            if (aligned && (unit + 2) * UNIT_SYMS <= n_sym && u + 1 < GROUP_UNITS) {
+                // whole units of an aligned input: mine comes from the registers filled one step ago
+                uint4 c0 = nx0, c1 = nx1;
+                if (!have_nx) {
+                    const uint8_t *src = in_bytes + (unit * UNIT_SYMS + lane * 16) * 2;
+                    c0 = ld_stream_v4(src); c1 = ld_stream_v4(src + 16);
+                }
+                const uint8_t *nsrc = in_bytes + ((unit + 1) * UNIT_SYMS + lane * 16) * 2;
+                nx0 = ld_stream_v4(nsrc); nx1 = ld_stream_v4(nsrc + 16);
+                have_nx = true;
+                const uint32_t w8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    len[j] = (uint32_t)s_len[fold16((j & 1) ? (w8[j >> 1] >> 16) : (w8[j >> 1] & 0xFFFFu))];
+            } else if (have_nx) {
+                // the last unit of the group (or of the whole units): its symbols are already here
+                have_nx = false;
+                const uint32_t w8[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    len[j] = (uint32_t)s_len[fold16((j & 1) ? (w8[j >> 1] >> 16) : (w8[j >> 1] & 0xFFFFu))];
+            } else {
+                uint32_t sym[16];
+                load_unit(in_bytes, n_sym, aligned, unit, lane, sym);
+#pragma unroll
+                for (int j = 0; j < 16; j++) len[j] = sym[j] > 0xFFFFu ? 0u : (uint32_t)s_len[fold16(sym[j])];
+            }
+            uint32_t L = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) L += len[j];
+            uint32_t off = L;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, o); if (lane >= o) off += y; }
+            off -= L;
+            // length of the code word before my first one (the previous lane's last; lane 0: the previous unit's last)
+            uint32_t plen = __shfl_up_sync(0xFFFFFFFFu, len[15], 1);
+            if (lane == 0) plen = u ? carry_len : (unit ? (uint32_t)s_len[fold16(in16[unit * UNIT_SYMS - 1])] : 0u);
+            carry_len = __shfl_sync(0xFFFFFFFFu, len[15], 31);      // (a ragged unit is the last one: never used then)
+            if (bits == 0) continue;
+            const unsigned long long sub0 = S / IDX_SUB_BITS;       // holds the unit's first bit
+            const uint32_t rel0 = (uint32_t)(S - sub0 * IDX_SUB_BITS);              // positions below are relative to sub0
+            const uint32_t nsub = (rel0 + bits - 1) / IDX_SUB_BITS + 1;
+            // the unit owns sub0 when its first code word is the first one of sub0
+            const bool own0 = unit == 0 || rel0 < __shfl_sync(0xFFFFFFFFu, plen, 0);
+            for (uint32_t i = lane; i < nsub; i += 32) acc[i] = 0;
+            __syncwarp();
+            {
+                uint32_t pos = rel0 + off;
+                uint32_t cur = 0xFFFFFFFFu, add = 0;                // run of code words in one subsequence
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // (a lane of a ragged last unit has len 0 from its first missing symbol on: those add nothing)
+                    const uint32_t sidx = pos / IDX_SUB_BITS;
+                    // the first code word of its subsequence: the one before it started in an earlier subsequence
+                    const bool first = (pos % IDX_SUB_BITS) < plen || (unit == 0 && lane == 0 && j == 0);
+                    if (sidx != cur) {
+                        if (add) atomicAdd(&acc[cur], add);
+                        cur = sidx; add = 0;
+                    }
+                    if (len[j]) add += (1u << 6) | (first ? (pos % IDX_SUB_BITS) & 63u : 0u);
+                    pos += len[j];
+                    if (len[j]) plen = len[j];
+                }
+                if (add) atomicAdd(&acc[cur], add);
+            }
+            __syncwarp();
+            // Subsequences that end inside the unit are complete: plain stores.  The first one when an earlier unit holds
+            // its first code word, and the last one (the units that follow add theirs), are shared: 32-bit atomic adds on
+            // the zeroed word that holds the 16-bit record (a count never carries into the neighbouring record).
+            for (uint32_t i = lane; i < nsub; i += 32) {
+                const uint32_t v = acc[i];
+                if (v == 0 || sub0 + i >= n_subs) continue;
+                const unsigned long long sub = sub0 + i;
+                if ((i == 0 && !own0) || i == nsub - 1)
+                    atomicAdd(reinterpret_cast<uint32_t *>(rec + (sub & ~1ull)), v << (16 * (uint32_t)(sub & 1)));
+                else
+                    rec[sub] = (uint16_t)v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// the workspace arrays of an encode of n_sym symbols (ctx->ws, behind the codebook workspace)
+static int enc2_work(Ctx *c, uint64_t n_sym, Enc2Work *W, uint64_t *ngroups_out, uint64_t *nblocks_out)
+{
     const uint64_t ngroups = (n_sym + GROUP_SYMS - 1) / GROUP_SYMS;
     const uint64_t nblocks = (ngroups + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK;
     if (nblocks > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_encode: input too large");
-    // the encode workspace sits behind the codebook workspace so the two never alias a live buffer
     const size_t off = 8u << 20;
     const size_t b_units = ((size_t)ngroups * GROUP_UNITS * 4 + 255) & ~(size_t)255;
     const size_t b_gbits = ((size_t)ngroups * 4 + 255) & ~(size_t)255;
@@ -522,11 +643,54 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     int rc = ensure_ws(c, off + b_units + b_gbits + b_gstart + b_blocks);
     if (rc) return rc;
     uint8_t *p = (uint8_t *)c->ws + off;
+    W->unit_bits = reinterpret_cast<uint32_t *>(p); p += b_units;
+    W->group_bits = reinterpret_cast<uint32_t *>(p); p += b_gbits;
+    W->group_start = reinterpret_cast<unsigned long long *>(p); p += b_gstart;
+    W->block_start = reinterpret_cast<unsigned long long *>(p);
+    *ngroups_out = ngroups;
+    *nblocks_out = nblocks;
+    return HF_OK;
+}
+
+// Records of the side index for the stream launch_encode has just packed with the same arguments (the unit and
+// group bit counts are still in the workspace).  d_rec: n_subs u16 records, zeroed here.
+int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, const uint8_t *d_stream,
+                        uint64_t start_bit, uint16_t *d_rec, uint64_t n_subs)
+{
+    const uint64_t n_sym = n_bytes / 2;
+    HF_CUDA(c, cudaMemsetAsync(d_rec, 0, n_subs * 2, c->stream));
+    if (n_sym == 0) return HF_OK;
     Enc2Work W;
-    W.unit_bits = reinterpret_cast<uint32_t *>(p); p += b_units;
-    W.group_bits = reinterpret_cast<uint32_t *>(p); p += b_gbits;
-    W.group_start = reinterpret_cast<unsigned long long *>(p); p += b_gstart;
-    W.block_start = reinterpret_cast<unsigned long long *>(p);
+    uint64_t ngroups, nblocks;
+    int rc = enc2_work(c, n_sym, &W, &ngroups, &nblocks);
+    if (rc) return rc;
+    if (!c->smem_attr[ATTR_INDEX]) {
+        HF_CUDA(c, cudaFuncSetAttribute(enc_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSYM));
+        c->smem_attr[ATTR_INDEX] = true;
+    }
+    d_stream += start_bit >> 3;
+    start_bit &= 7;
+    const unsigned long long bit0 = ((uintptr_t)d_stream & 15) * 8ull + start_bit;     // frame bit of the first code word
+    const uint64_t bw = BITS_THREADS / 32;
+    uint64_t grid = (ngroups + bw - 1) / bw;
+    if (grid > (uint64_t)(3 * c->sm_count)) grid = 3 * c->sm_count;
+    HF_PROF(c, "enc_index_kernel"); enc_index_kernel<<<(unsigned)grid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, bit0, d_rec, n_subs);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
+                  uint64_t start_bit, uint32_t maxlen_hint)
+{
+    (void)maxlen_hint;
+    const uint64_t n_sym = n_bytes / 2;
+    if (n_sym == 0) return HF_OK;
+    if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
+    if ((uintptr_t)d_cb & 15) return set_err(c, HF_ERR_ARG, "hf_encode: codebook must be 16-byte aligned");
+    Enc2Work W;
+    uint64_t ngroups, nblocks;
+    int rc = enc2_work(c, n_sym, &W, &ngroups, &nblocks);
+    if (rc) return rc;
 
     if (!c->smem_attr[ATTR_ENCODE]) {
         HF_CUDA(c, cudaFuncSetAttribute(encode2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM));

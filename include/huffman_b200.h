@@ -191,6 +191,21 @@ int hf_set_decode_mode(hf_ctx *ctx, int exact_only);
 int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8_t *d_out,
                   uint64_t capacity, uint64_t *h_out_bytes);
 
+/* ---- optional side index -------------------------- */
+
+/* The reference format has no offset array (Decompressor.cu:259-284 decodes serially), so hf_decompress finds the code
+ * word boundaries by self-synchronisation.  For an image THIS library writes, the compressor can also produce a side
+ * index — one 16-bit record per 256 bits of payload (first code word boundary, code words starting there), 1/16 of the
+ * image — with which the decoder skips the synchronisation pass.  The image itself is unchanged (byte-identical to
+ * the reference's); the index is never required: hf_decompress_indexed checks it against the image and against
+ * every walk it drives, and decodes without it when it is absent, stale, made for another alignment of the image
+ * (address modulo 16) or wrong.  d_index must be 16-byte aligned. */
+uint64_t hf_index_bound(uint64_t n_bytes);        /* safe capacity for the index of an n_bytes input */
+int hf_compress_indexed(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, uint8_t *d_file, uint64_t capacity,
+                        uint64_t *h_file_bytes, uint8_t *d_index, uint64_t index_capacity, uint64_t *h_index_bytes);
+int hf_decompress_indexed(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, const uint8_t *d_index,
+                          uint64_t index_bytes, uint8_t *d_out, uint64_t capacity, uint64_t *h_out_bytes);
+
 /* ---- host-buffer calls (what the CLIs and the end-to-end benchmark use) - */
 
 /* h_in / h_file should be pinned (hf_host_alloc) for full PCIe speed; pageable works.

@@ -461,6 +461,55 @@ def test_round_trip_across_chunk_and_group_boundaries(codec, oracle):
     assert np.array_equal(codec.compress(dev(base)).cpu().numpy(), img_full)
 
 
+# ---------------------------------------------------------------- side index (row f3)
+@pytest.mark.parametrize("name", list(CASES))
+def test_side_index_small_cases(codec, oracle, name):
+    data = CASES[name]
+    d = dev(data) if data.size else torch.zeros(0, dtype=torch.uint8, device="cuda")
+    image, index = codec.compress_indexed(d)
+    assert np.array_equal(image.cpu().numpy(), oracle.compress(data))           # the image does not change
+    back = codec.decompress_indexed(image, index)
+    assert np.array_equal(back.cpu().numpy(), data)
+
+
+def test_side_index_large_and_never_required(codec, oracle):
+    rng = np.random.default_rng(9)
+    parts = [synth.mixed(24 << 20, seg_bytes=1 << 20), np.full(3 << 20, 0x20, np.uint8), synth.zipf_bytes((5 << 20) + 1, 1.2, 77)]
+    data = np.concatenate(parts)
+    d = dev(data)
+    image, index = codec.compress_indexed(d)
+    assert np.array_equal(image.cpu().numpy(), codec.compress(d).cpu().numpy())
+    assert index.numel() > 64 and index.numel() <= image.numel() // 16 + 2 * 16384 + 64
+    # with the index, and what its records must be: the same a self-synchronising decode finds
+    prof_on = codec.profile(True)
+    back = codec.decompress_indexed(image, index)
+    prof = codec.profile_read()
+    codec.profile(False)
+    assert torch.equal(back, d)
+    assert "dec_sync3_kernel" not in prof and "dec_write3_kernel" in prof       # the synchronisation pass was skipped
+    # a stale or damaged index is noticed and ignored
+    bad = index.clone()
+    pos = 64 + 2 * int(rng.integers(1000, bad.numel() // 2 - 1000))
+    bad[pos:pos + 64] = 0
+    assert torch.equal(codec.decompress_indexed(image, bad), d)
+    bad = index.clone()
+    bad[0] ^= 0xFF                                                               # magic
+    assert torch.equal(codec.decompress_indexed(image, bad), d)
+    other_image, other_index = codec.compress_indexed(dev(data[: 20 << 20]))
+    assert torch.equal(codec.decompress_indexed(image, other_index), d)
+    # the image at another alignment: the records were made for the original one
+    buf = torch.zeros(image.numel() + 64, dtype=torch.uint8, device="cuda")
+    buf[8:8 + image.numel()] = image
+    assert torch.equal(codec.decompress_indexed(buf[8:8 + image.numel()], index), d)
+    # long codes (slow table paths) with an index
+    h = fibonacci_hist(45)
+    syms = np.flatnonzero(h).astype(np.uint16)
+    long_data = np.concatenate([rng.choice(syms, 300000, p=h[syms] / h[syms].sum()), syms, syms[::-1]]).astype(np.uint16).view(np.uint8)
+    image, index = codec.compress_indexed(dev(long_data))
+    assert np.array_equal(image.cpu().numpy(), oracle.compress(long_data))
+    assert np.array_equal(codec.decompress_indexed(image, index).cpu().numpy(), long_data)
+
+
 # ---------------------------------------------------------------- full-size properties (configs 4 and 5)
 def test_zipf1g_properties(codec, oracle):
     n = 1 << 30
