@@ -510,7 +510,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
 // A unit writes the records of the subsequences that end inside it with plain stores and adds its share of the two
 // it shares with its neighbours with one atomic each (the records are zeroed first).  Reads N, writes C / 16.
 constexpr uint32_t IDX_SUB_BITS = 256;                              // = SUB_BITS of the decoder
-constexpr uint32_t IDX_SUBS_MAX = 160;                              // a unit spans <= 512 * 64 / 256 + 2 subsequences
+constexpr uint32_t IDX_SUBS_MAX = 160;                              // a unit spans <= 512 * 64 / 256 + 2 subsequences (+ 1)
 
 __global__ void __launch_bounds__(BITS_THREADS)
 enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, Enc2Work W,
@@ -590,36 +590,39 @@ enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Cod
             const uint32_t nsub = (rel0 + bits - 1) / IDX_SUB_BITS + 1;
             // the unit owns sub0 when its first code word is the first one of sub0
             const bool own0 = unit == 0 || rel0 < __shfl_sync(0xFFFFFFFFu, plen, 0);
-            for (uint32_t i = lane; i < nsub; i += 32) acc[i] = 0;
+            // acc[i] = ((unit-relative index of the first code word of subsequence sub0 + i) << 8) | its bit offset + 1,
+            // written by the one lane that holds that code word; 0 = none of my code words starts there
+            for (uint32_t i = lane; i <= nsub; i += 32) acc[i] = 0;
             __syncwarp();
             {
                 uint32_t pos = rel0 + off;
-                uint32_t cur = 0xFFFFFFFFu, add = 0;                // run of code words in one subsequence
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    // (a lane of a ragged last unit has len 0 from its first missing symbol on: those add nothing)
-                    const uint32_t sidx = pos / IDX_SUB_BITS;
-                    // the first code word of its subsequence: the one before it started in an earlier subsequence
-                    const bool first = (pos % IDX_SUB_BITS) < plen || (unit == 0 && lane == 0 && j == 0);
-                    if (sidx != cur) {
-                        if (add) atomicAdd(&acc[cur], add);
-                        cur = sidx; add = 0;
-                    }
-                    if (len[j]) add += (1u << 6) | (first ? (pos % IDX_SUB_BITS) & 63u : 0u);
+                    // first code word of its subsequence: the one before it started in an earlier subsequence
+                    // (a lane of a ragged last unit has len 0 from its first missing symbol on: never first)
+                    const uint32_t inb = pos % IDX_SUB_BITS;
+                    const bool first = len[j] != 0 && (inb < plen || (unit == 0 && lane == 0 && j == 0));
+                    if (first) acc[pos / IDX_SUB_BITS] = ((lane * 16 + j) << 8) | ((inb & 63u) + 1u);
+                    plen = len[j];
                     pos += len[j];
-                    if (len[j]) plen = len[j];
                 }
-                if (add) atomicAdd(&acc[cur], add);
             }
             __syncwarp();
-            // Subsequences that end inside the unit are complete: plain stores.  The first one when an earlier unit holds
-            // its first code word, and the last one (the units that follow add theirs), are shared: 32-bit atomic adds on
-            // the zeroed word that holds the 16-bit record (a count never carries into the neighbouring record).
+            // Counts are differences of first-code-word indices.  Subsequences that end inside the unit are complete:
+            // plain stores.  The first one when an earlier unit holds its first code word, and the last one (the units
+            // that follow add theirs), are shared: 32-bit atomic adds on the zeroed word that holds the 16-bit record
+            // (a count never carries into the neighbouring record).
+            const uint32_t nsym_unit = (uint32_t)min((uint64_t)UNIT_SYMS, n_sym - unit * UNIT_SYMS);
             for (uint32_t i = lane; i < nsub; i += 32) {
-                const uint32_t v = acc[i];
-                if (v == 0 || sub0 + i >= n_subs) continue;
+                const uint32_t a = acc[i], nx = i + 1 < nsub ? acc[i + 1] : 0u;
                 const unsigned long long sub = sub0 + i;
-                if ((i == 0 && !own0) || i == nsub - 1)
+                if (sub >= n_subs) continue;
+                const uint32_t end = nx ? (nx >> 8) : nsym_unit;    // (only the unit's last subsequence can be without a first)
+                uint32_t v;
+                if (a) v = ((a & 0xFFu) - 1u) | ((end - (a >> 8)) << 6);
+                else if (i == 0) v = end << 6;                      // my code words before the first boundary: the owner's
+                else continue;                                      // my last bits belong to a code word of the one before
+                if (a == 0 || nx == 0)
                     atomicAdd(reinterpret_cast<uint32_t *>(rec + (sub & ~1ull)), v << (16 * (uint32_t)(sub & 1)));
                 else
                     rec[sub] = (uint16_t)v;
