@@ -686,7 +686,7 @@ int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, 
         return HF_OK;
     }
 
-    DecodeJob job;
+    DecodeJob job{};
     rc = decode_begin(c, d_file, file_bytes, info.payload_start_bit, nsym, tab, d_out, &job);
     if (rc) return rc;
     const uint64_t frame_off = (uint64_t)(job.frame - d_file);          // file byte of frame byte 0

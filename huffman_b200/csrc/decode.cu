@@ -169,7 +169,7 @@ dec_parse_kernel(const uint8_t *__restrict__ file, unsigned long long file_bytes
     extern __shared__ uint8_t sm[];
     __shared__ unsigned long long s_pos;                // bit position (from the stream start) of the next entry
     __shared__ uint32_t s_k, s_done, s_err;
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x;
 
     uint32_t U = 0, is_odd = 0, last = 0, pre = 3;
     bool ok = file_bytes >= 3;
@@ -521,7 +521,7 @@ int launch_decode_indexed(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes
                           const DecodeTable *d_tab, uint8_t *d_out, const uint16_t *d_rec, uint64_t n_subs)
 {
     if (n_symbols == 0) return HF_OK;
-    DecodeJob job;
+    DecodeJob job{};
     int rc = decode_begin(c, d_stream, stream_bytes, start_bit, n_symbols, d_tab, d_out, &job);
     if (rc) return rc;
     if (n_subs != job.nch * DEC_THREADS) return set_err(c, HF_ERR_FORMAT, "index does not fit the stream");
@@ -552,7 +552,7 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
                   uint64_t n_symbols, const DecodeTable *d_tab, uint8_t *d_out)
 {
     if (n_symbols == 0) return HF_OK;
-    DecodeJob job;
+    DecodeJob job{};
     int rc = decode_begin(c, d_stream, stream_bytes, start_bit, n_symbols, d_tab, d_out, &job);
     if (rc) return rc;
     return decode_slice(c, job, 0, job.nch);

@@ -588,8 +588,6 @@ enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Cod
             const unsigned long long sub0 = S / IDX_SUB_BITS;       // holds the unit's first bit
             const uint32_t rel0 = (uint32_t)(S - sub0 * IDX_SUB_BITS);              // positions below are relative to sub0
             const uint32_t nsub = (rel0 + bits - 1) / IDX_SUB_BITS + 1;
-            // the unit owns sub0 when its first code word is the first one of sub0
-            const bool own0 = unit == 0 || rel0 < __shfl_sync(0xFFFFFFFFu, plen, 0);
             // acc[i] = ((unit-relative index of the first code word of subsequence sub0 + i) << 8) | its bit offset + 1,
             // written by the one lane that holds that code word; 0 = none of my code words starts there
             for (uint32_t i = lane; i <= nsub; i += 32) acc[i] = 0;

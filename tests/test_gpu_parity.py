@@ -250,6 +250,44 @@ def test_malformed_images_are_rejected(codec, oracle, romeo):
         codec.decompress(dev(bad))
 
 
+
+def test_damaged_images_end_in_an_error_or_an_output(codec, oracle, romeo):
+    """bit flips in the table, in the payload, in the size field, and truncations: HF_ERR_* or some output within
+    the capacity, and the context keeps decoding good images (the reference aborts or reads out of bounds here)"""
+    from huffman_b200 import HuffmanError
+    rng = np.random.default_rng(99)
+    bases = [romeo, synth.zipf1g(128 << 10), np.repeat(rng.integers(0, 4, 2000, dtype=np.uint8), 41)]
+    seen = {"error": 0, "output": 0}
+    for data in bases:
+        good_np = oracle.compress(data)
+        good, d = dev(good_np), dev(data)
+        _, info = codec.parse_header(good)
+        hdr = max(4, int(info.payload_start_bit) // 8)
+        out = torch.empty(data.size + 4096, dtype=torch.uint8, device="cuda")
+        for t in range(60):
+            img = good_np.copy()
+            kind = t % 4
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    img[int(rng.integers(0, hdr))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                for _ in range(int(rng.integers(1, 20))):
+                    img[int(rng.integers(hdr, img.size))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 2:
+                img = img[: int(rng.integers(1, img.size))]
+            else:
+                img[hdr - int(rng.integers(1, 9))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                back = codec.decompress(dev(img), out)
+                assert back.numel() <= out.numel()
+                seen["output"] += 1
+            except HuffmanError:
+                seen["error"] += 1
+        back = codec.decompress(good, out)
+        assert back.numel() == data.size and torch.equal(back, d)
+    assert seen["error"] and seen["output"]
+
+
 # ---------------------------------------------------------------- sharded stream (row e), ranks emulated on one GPU
 def _decode_by_ranges(codec, image_np, cuts, exact_mode):
     """splits the image at the byte offsets `cuts` and decodes every range on its own, as the ranks of a sharded
