@@ -246,6 +246,20 @@ constexpr uint32_t SEG_BITS = 128;                              // checkpoint sp
 constexpr uint32_t NSEG = SPAN_BITS / SEG_BITS;                 // 8
 constexpr size_t S3_SMEM = (4u << MICRO_K) + (size_t)S3_THREADS * ROW_WORDS * 4;
 
+// the 32-bit shared address of p, passed through a shuffle so that the compiler keeps it in a register instead of
+// re-deriving it (S2UR SR_CgaCtaId + three uniform ops) at every use; call with the whole warp
+__device__ __forceinline__ uint32_t opaque_shared_addr(const void *p)
+{
+    return __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(p), 0);
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+    return v;
+}
+
 // Record of a walk: chkpos byte k = (first code word boundary at or after bit 128k) - 128k; chkcnt byte k = code
 // words starting in [128k, 128k + 128).  CHK_NONE (bytes 0xFF, no checkpoint offset is that large) = no walk yet.
 struct Chk { uint32_t pos[2], cnt[2]; };
@@ -254,13 +268,16 @@ constexpr uint32_t CHK_NONE = 0xFFFFFFFFu;
 // Walks the code words of a span from bit `start` to `lim`.  RESYNC: `rec` describes an earlier walk; stop at
 // the first checkpoint both walks share and keep the earlier record from there on (`end` stays the earlier one's).
 template <bool RESYNC>
-__device__ __forceinline__ void walk_span(const uint32_t *row, const uint32_t *s_t14, const DecodeTable *tab,
+__device__ __forceinline__ void walk_span(const uint32_t *row, uint32_t t14_a, const DecodeTable *tab,
                                           const uint8_t *frame, unsigned long long frame_bytes,
                                           unsigned long long span_bit0, uint32_t k2shift, uint32_t start, uint32_t lim,
                                           Chk &rec, uint32_t &end, uint32_t &bad)
 {
     uint32_t pos = start, n = 0, wl = lim;
     uint32_t npos[2] = {0, 0}, ncnt[2] = {0, 0};
+    // t14_a: the table's 32-bit shared address as a plain register value (opaque_shared_addr); left to itself the
+    // compiler rebuilds the shared window base inside every walk loop, four uniform instructions per code word
+    const uint32_t row_a = (uint32_t)__cvta_generic_to_shared(row);
     int kept = NSEG;                                    // checkpoints >= kept keep the earlier record
 #pragma unroll
     for (int k = 0; k < (int)NSEG; k++) {
@@ -272,21 +289,17 @@ __device__ __forceinline__ void walk_span(const uint32_t *row, const uint32_t *s
         npos[k >> 2] |= rel << (8 * (k & 3));
         const uint32_t lw = min(wl, SEG_BITS * (k + 1));
         while (pos < lw) {
-            const uint32_t *wp = row + (pos >> 5);
-            const uint32_t win = __funnelshift_l(wp[1], wp[0], pos);
-            const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];         // the d14 plane
-            uint32_t len;
-            if ((e14 & 0xFu) != 0xCu) {
-                len = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);   // micro tree: 2 bits per slot
-            } else {
-                len = e14 >> 4;
+            const uint32_t wa = row_a + ((pos >> 5) << 2);
+            const uint32_t win = __funnelshift_l(lds32(wa + 4), lds32(wa), pos);
+            const uint32_t e14 = lds32(t14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));    // the d14 plane
+            const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
+            uint32_t len = ((e14 & 0xFu) != 0xCu) ? deep : (e14 >> 4);
+            if (len == 0) {
+                len = __ldg(tab->lenflat + (win >> k2shift));
                 if (len == 0) {
-                    len = __ldg(tab->lenflat + (win >> k2shift));
-                    if (len == 0) {
-                        const uint32_t e = slow_decode(tab, frame, frame_bytes, span_bit0 + pos);
-                        bad |= e >> 31;
-                        len = e & 0x7Fu;
-                    }
+                    const uint32_t e = slow_decode(tab, frame, frame_bytes, span_bit0 + pos);
+                    bad |= e >> 31;
+                    len = e & 0x7Fu;
                 }
             }
             pos += len;
@@ -335,7 +348,7 @@ struct SyncCtx {
     unsigned long long frame_bytes, F0, range_end_bit, nch;
     const DecodeTable *tab;
     DecWork *work;
-    const uint32_t *s_t14;
+    uint32_t t14_a;                     // shared address of the d14 plane (opaque_shared_addr)
     uint32_t *s_bits, *s_wend, *s_red;
     uint32_t g, k2shift;                // gcd of the code lengths (1 when speculating), 32 - k2
 };
@@ -349,7 +362,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
     const unsigned long long frame_bytes = S.frame_bytes, F0 = S.F0, range_end_bit = S.range_end_bit, nch = S.nch;
     const DecodeTable *tab = S.tab;
     DecWork *work = S.work;
-    const uint32_t *s_t14 = S.s_t14;
+    const uint32_t t14_a = S.t14_a;
     uint32_t *s_bits = S.s_bits, *s_wend = S.s_wend, *s_red = S.s_red;
     const uint32_t g = S.g, k2shift = S.k2shift;
     DecLayout L(work, nch);
@@ -397,7 +410,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
         nwalk++;
     };
     if (lim) {
-        if (p < lim) { walk_span<false>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
+        if (p < lim) { walk_span<false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
         else end = p - lim;
         rec_end = end;
     }
@@ -425,7 +438,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
                     end = hit & 0xFFu;              // rec stays with the walk it describes
                 } else if (q < lim) {
                     end = rec_end;                  // a merge keeps the recorded walk's end
-                    walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                    walk_span<true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
                     rec_p = q; rec_end = end;
                     memo_add(q, end);
                 } else {
@@ -443,7 +456,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
     if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
         if (p < lim) {
             end = rec_end;
-            walk_span<true>(row, s_t14, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            walk_span<true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
         } else {
             rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
         }
@@ -503,7 +516,7 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
     }
-    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, s_t14, s_bits, s_wend, s_red,
+    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, opaque_shared_addr(s_t14), s_bits, s_wend, s_red,
                     speculative ? 1u : tab->len_gcd, 32u - tab->k2};
     uint32_t bad = 0;
     __syncthreads();                                    // planes loaded
@@ -541,7 +554,7 @@ dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_b
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
     }
-    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, s_t14, s_bits, s_wend, s_red,
+    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, opaque_shared_addr(s_t14), s_bits, s_wend, s_red,
                     speculative ? 1u : tab->len_gcd, 32u - tab->k2};
     uint32_t bad = 0;
     __syncthreads();

@@ -41,6 +41,14 @@ constexpr unsigned long long NOT_FINAL = ~0ull;
 
 __device__ __forceinline__ uint32_t fold16(uint32_t sym) { return sym ^ (sym >> 8); }      // involution on 16 bits
 
+// shared-memory loads by 32-bit shared address (taken once with __cvta_generic_to_shared)
+__device__ __forceinline__ uint32_t lds8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
 struct Enc2Work {                       // device arrays in ctx->ws
     uint32_t *unit_bits;                // [ngroups * 32]
     uint32_t *group_bits;               // [ngroups]
@@ -79,6 +87,7 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
     }
     __syncthreads();
     const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const uint32_t len_a = (uint32_t)__cvta_generic_to_shared(s_len);
     const uint64_t warp0 = (uint64_t)blockIdx.x * (BITS_THREADS / 32) + (tid >> 5);
     const uint64_t nwarps = (uint64_t)gridDim.x * (BITS_THREADS / 32);
     for (uint64_t g = warp0; g < ngroups; g += nwarps) {
@@ -87,7 +96,13 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
         for (uint32_t u = 0; u < GROUP_UNITS; u++) {
             const uint64_t unit = g * GROUP_UNITS + u;
             uint32_t t = 0;
-            if (unit * UNIT_SYMS < n_sym) {
+            if ((unit + 1) * UNIT_SYMS <= n_sym) {              // a whole unit: no per-symbol end test (a predicated
+                uint32_t sym[16];                               // lookup makes the compiler rebuild the shared base
+                load_unit(in_bytes, n_sym, aligned, unit, lane, sym);       // address for every symbol)
+#pragma unroll
+                for (int j = 0; j < 16; j++) t += lds8(len_a + fold16(sym[j]));
+                t = __reduce_add_sync(0xFFFFFFFFu, t);
+            } else if (unit * UNIT_SYMS < n_sym) {
                 uint32_t sym[16];
                 load_unit(in_bytes, n_sym, aligned, unit, lane, sym);
 #pragma unroll
