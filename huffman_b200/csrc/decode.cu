@@ -460,7 +460,7 @@ static int launch_scan(Ctx *c, DecWork *work, unsigned long long nch, unsigned l
 }
 
 // The decode kernels over the chunks [c0, c1) of the frame: the whole stream in one go, or one slice of a pipelined
-// host-buffer decode (slices in ascending order; c0 a multiple of 2).
+// host-buffer decode (slices in ascending order; c0 a multiple of GROUP_CHUNKS).
 static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                                unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
                                uint16_t *out16, DecWork *work, unsigned long long nch, unsigned long long c0,
@@ -477,7 +477,7 @@ static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long 
 
 // A decode of one stream, all at once (launch_decode) or in slices of chunks as its bytes arrive from the host
 // (hf_decompress_host): decode_begin lays out the frame and the work area, decode_slice runs the exact kernels on
-// the chunks [c0, c1) — slices in ascending order, c0 a multiple of 2.  job.total is the device address of the
+// the chunks [c0, c1) — slices in ascending order, c0 a multiple of GROUP_CHUNKS.  job.total is the device address of the
 // running symbol count (symbols decoded by the slices so far).
 int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_t start_bit, uint64_t n_symbols,
                  const DecodeTable *d_tab, uint8_t *d_out, DecodeJob *job)
@@ -595,10 +595,9 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
         rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true);
         if (rc) return rc;
         {
-            // the (up to) 8 groups of the tail converge one by one on guessed starts; the repair carries the chain
-            // from the first of them (the lead-in, 224 KiB or more when the range is that long) to the range end
-            const unsigned long long ngroups = (nch + 1) / 2, g_first = ngroups > 8 ? ngroups - 8 : 0;
-            rc = launch_fix2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, (g_first + 1) * 2, nch, true);
+            // the groups of the tail converge one by one on guessed starts; the repair carries the chain from the
+            // first of them (the lead-in, 240 KiB or more when the range is that long) to the range end
+            rc = launch_fix2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, tail_first_chunk(nch) + GROUP_CHUNKS, nch, true);
             if (rc) return rc;
         }
     } else {

@@ -230,17 +230,18 @@ __device__ __forceinline__ void load_sub(uint32_t (&r)[9], const uint8_t *frame,
 // A thread walks a SPAN of 4 subsequences (1024 bits).  Longer spans mean fewer repeated walks: a walk
 // from a wrong start re-joins the true one after tens of bits on skewed codes but only after ~2,000 bits
 // on the nearly fixed-length codes of flat data, and every subsequence a wrong walk crosses costs the
-// fix-point one more round.  A CTA of 1024 threads stages a GROUP of 8 chunks (128 KiB) in shared memory,
-// one padded row of 33 words per thread (bank = (thread + word) mod 32; the pad word repeats the next
-// row's first word so a 32-bit window never leaves the row).
+// fix-point one more round.  A CTA of 1024 threads holds 8 TEAMS of 4 warps; a team stages its own GROUP (one
+// chunk, 16 KiB) in shared memory, one padded row of 33 words per thread (bank = (thread + word) mod 32; the pad
+// word repeats the next row's first word so a 32-bit window never leaves the row), and converges on it behind its
+// own named barrier.  Small teams wait less on their slowest warp (teams of 8 warps: +7 % kernel time, of 16: +15 %);
+// the price is one more group boundary per chunk for the repair pass, which is cheap.
 constexpr int S3_THREADS = 1024;
-constexpr int TEAM_THREADS = 256;                               // a team of 8 warps works on its own group
+constexpr int TEAM_THREADS = DEC_TEAM_THREADS;
 constexpr int S3_TEAMS = S3_THREADS / TEAM_THREADS;
-constexpr uint32_t SPAN_SUBS = 4;
+constexpr uint32_t SPAN_SUBS = DEC_SPAN_SUBS;
 constexpr uint32_t SPAN_BITS = SPAN_SUBS * SUB_BITS;            // 1024
 constexpr uint32_t SPAN_WORDS = SPAN_BITS / 32;                 // 32
 constexpr uint32_t ROW_WORDS = SPAN_WORDS + 1;
-constexpr uint32_t GROUP_CHUNKS = TEAM_THREADS * SPAN_SUBS / DEC_THREADS;  // 2
 constexpr unsigned long long GROUP_BITS = (unsigned long long)TEAM_THREADS * SPAN_BITS;
 constexpr uint32_t SEG_BITS = 128;                              // checkpoint spacing
 constexpr uint32_t NSEG = SPAN_BITS / SEG_BITS;                 // 8
@@ -353,7 +354,7 @@ struct SyncCtx {
     uint32_t g, k2shift;                // gcd of the code lengths (1 when speculating), 32 - k2
 };
 
-// One team converges on one group (2 chunks, 32 KiB): per-subsequence records, chunk totals and overflows.
+// One team converges on one group (GROUP_CHUNKS chunks): per-subsequence records, chunk totals and overflows.
 // exact: the group's first code word starts `start` bits into it (the stream head, or the true overflow of the group
 // before when a group is redone); otherwise the first span starts from a guess like every other one.
 __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long grp, bool exact, uint32_t start, uint32_t &bad)
@@ -372,7 +373,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
     uint32_t *team_rows = s_bits + team * TEAM_THREADS * ROW_WORDS;
 
     team_sync(team);                                // my team's rows, s_wend, s_red are free again
-    // ---- stage the group's 32 KiB: 8 coalesced 128-bit loads per thread ----
+    // ---- stage the group: 8 coalesced 128-bit loads per thread ----
     const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
 #pragma unroll
     for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
@@ -973,9 +974,9 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
         c->smem_attr[ATTR_SYNC] = true;
     }
     unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
-    // tail_only: the overflow past the range end, speculatively from a guessed start up to eight groups
-    // (224 .. 256 KiB of self-synchronisation) before it
-    unsigned long long g_first = tail_only ? (ngroups > 8 ? ngroups - 8 : 0) : 0;
+    // tail_only: the overflow past the range end, speculatively from a guessed start TAIL_CHUNKS chunks
+    // (240 .. 256 KiB of self-synchronisation) before it
+    unsigned long long g_first = tail_only ? tail_first_chunk(nch) / GROUP_CHUNKS : 0;
     if (!tail_only) {
         if (c0 % GROUP_CHUNKS) return set_err(c, HF_ERR_INTERNAL, "decode slice does not start at a group");
         g_first = c0 / GROUP_CHUNKS;

@@ -38,6 +38,21 @@ __device__ __forceinline__ unsigned long long peek64(const F &f, uint32_t bitpos
 constexpr int DEC_THREADS = 512;
 constexpr uint32_t SUB_BITS = 256;                              // bits per subsequence (thread)
 constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits = 16 KiB
+// the synchronisation kernel's unit of convergence: a team of DEC_TEAM_THREADS threads, DEC_SPAN_SUBS subsequences each
+#ifndef HF_TEAM_THREADS
+#define HF_TEAM_THREADS 128
+#endif
+constexpr int DEC_TEAM_THREADS = HF_TEAM_THREADS;
+constexpr uint32_t DEC_SPAN_SUBS = 4;
+constexpr uint32_t GROUP_CHUNKS = DEC_TEAM_THREADS * DEC_SPAN_SUBS / DEC_THREADS;   // 1
+static_assert(GROUP_CHUNKS >= 1 && GROUP_CHUNKS * DEC_THREADS == DEC_TEAM_THREADS * DEC_SPAN_SUBS, "a group is whole chunks");
+// a speculative range call (hf_range_overflow) works on the last TAIL_CHUNKS chunks of the range, from a group boundary
+constexpr unsigned long long TAIL_CHUNKS = 16;
+__host__ __device__ inline unsigned long long tail_first_chunk(unsigned long long nch)
+{
+    const unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS, tg = TAIL_CHUNKS / GROUP_CHUNKS;
+    return (ngroups > tg ? ngroups - tg : 0) * GROUP_CHUNKS;
+}
 
 
 struct DecWork {
