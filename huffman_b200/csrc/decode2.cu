@@ -710,15 +710,22 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             // flush [w0, wend): staging slots [mis, mis + n)
             const uint32_t n = wend - w0;
             uint16_t *dst = out + base + w0 - mis;      // 16-byte aligned when out is
-            const uint32_t nvec = (mis + n + 7) / 8;
-            for (uint32_t q = lane; q < nvec; q += 32) {
-                const uint32_t j0 = q * 8;
-                if (j0 >= mis && j0 + 8 <= mis + n && (((uintptr_t)(dst + j0) & 15) == 0)) {
-                    st_stream_v4(dst + j0, reinterpret_cast<const uint4 *>(sout)[q]);
-                } else {
-                    for (uint32_t j = j0; j < j0 + 8; j++)
-                        if (j >= mis && j < mis + n) dst[j] = sout[j];
+            const uint32_t endslot = mis + n, nvec = (endslot + 7) / 8;
+            if (((uintptr_t)dst & 15) == 0) {
+                for (uint32_t q = lane; q < nvec; q += 32) {
+                    const uint32_t j0 = q * 8;
+                    if (j0 >= mis && j0 + 8 <= endslot) st_stream_v4(dst + j0, reinterpret_cast<const uint4 *>(sout)[q]);
                 }
+                // the partial vectors at the two ends, a symbol per lane: lanes 0-7 the first vector when it is
+                // partial, lanes 8-15 the last one when it is partial and not the first
+                const uint32_t last0 = endslot & ~7u;
+                const uint32_t j = lane < 8 ? lane : last0 + (lane - 8);
+                const bool part = lane < 8 ? (mis != 0 || endslot < 8) : (lane < 16 && last0 != 0 && (endslot & 7u) != 0);
+                if (part && j >= mis && j < endslot) dst[j] = sout[j];
+            } else {
+                for (uint32_t q = lane; q < nvec; q += 32)
+                    for (uint32_t j = q * 8; j < q * 8 + 8; j++)
+                        if (j >= mis && j < endslot) dst[j] = sout[j];
             }
             __syncwarp();
         }
