@@ -404,14 +404,16 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             uint32_t v[16];
             uint32_t L = 0;
             uint4 nxt0 = cur0, nxt1 = cur1;
+            uint32_t tail_sym = 0;
             if (fast) {
                 if (!have_cur) {
                     const uint8_t *src = in_bytes + (unit * UNIT_SYMS + lane * 16) * 2;
                     cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
                 }
-                {   // the next unit's symbols: prefetched for the next step, and lane 0 completes my last word with them
+                {   // the next unit's symbols: prefetched for the next step; its first 16, one per lane, complete my last word
                     const uint8_t *src = in_bytes + ((unit + 1) * UNIT_SYMS + lane * 16) * 2;
                     nxt0 = ld_stream_v4(src); nxt1 = ld_stream_v4(src + 16);
+                    tail_sym = reinterpret_cast<const uint16_t *>(in_bytes)[(unit + 1) * UNIT_SYMS + (lane & 15)];
                 }
                 const uint32_t w8[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
                 uint32_t zero = 0xFFFFFFFFu;
@@ -458,35 +460,35 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 }
             }
             __syncwarp();
-            // ---- lane 0 completes my last, partial word with the codes that follow (the next unit's first symbols) ----
-            if (lane == 0) {
-                uint32_t have = end_rel & 31;                       // bits of my last word that are mine
-                if (have) {
-                    uint32_t word = 0;
-                    const uint32_t n8[8] = {nxt0.x, nxt0.y, nxt0.z, nxt0.w, nxt1.x, nxt1.y, nxt1.z, nxt1.w};
+            // ---- my last, partial word is completed with the codes that follow (the next unit's first symbols): lanes
+            // 0-15 look one symbol up each and OR their code in where it starts inside the word ----
+            const uint32_t have0 = end_rel & 31;                    // bits of my last word that are mine
+            if (have0) {
+                uint32_t x = 0, l = 0;
+                if (lane < 16) {
+                    const uint32_t f = fold16(tail_sym);
+                    x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
+                    l = 31 - __clz(x | 1u);
+                }
+                uint32_t o = l;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        if (have < 32) {
-                            const uint32_t sj = (j & 1) ? (n8[j >> 1] >> 16) : (n8[j >> 1] & 0xFFFFu);
-                            uint32_t len;
-                            unsigned long long code;
-                            lookup_any(p16, p8, cb, sj, len, code);
-                            if (len) {
-                                const unsigned long long left = code << (64 - len);    // left aligned
-                                word |= (uint32_t)(left >> 32) >> have;
-                                have += len;
-                            }
-                        }
-                    }
-                    // sixteen codes did not fill the word (one- and two-bit codes): go on from the input; the next
-                    // unit is whole, so the word does fill up before the input ends
+                for (int d = 1; d < 16; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, o, d); if (lane >= d) o += y; }
+                const uint32_t tot16 = __shfl_sync(0xFFFFFFFFu, o, 15);
+                const bool odd = __any_sync(0xFFFFFFFFu, lane < 16 && x == 0);     // a code that is not in the shared table
+                if (!odd && have0 + tot16 >= 32) {
+                    const uint32_t at = have0 + o - l;              // where my code starts in the word
+                    red_or_if(lane < 16 && at < 32, sbase + 4u * own_hi, (x << (32 - l)) >> at);    // the leading one falls off
+                } else if (lane == 0) {
+                    // long codes, or sixteen one- and two-bit codes that do not fill the word: one lane, from the input;
+                    // the next unit is whole, so the word does fill up before the input ends
+                    uint32_t have = have0, word = 0;
                     const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
-                    for (uint64_t sx = (unit + 1) * UNIT_SYMS + 16; have < 32 && sx < n_sym; sx++) {
+                    for (uint64_t sx = (unit + 1) * UNIT_SYMS; have < 32 && sx < n_sym; sx++) {
                         uint32_t len;
                         unsigned long long code;
                         lookup_any(p16, p8, cb, in16[sx], len, code);
                         if (len) {
-                            const unsigned long long left = code << (64 - len);
+                            const unsigned long long left = code << (64 - len);    // left aligned
                             word |= (uint32_t)(left >> 32) >> have;
                             have += len;
                         }
