@@ -31,7 +31,10 @@ constexpr uint32_t UNIT_SYMS = 512;
 constexpr uint32_t GROUP_UNITS = 32;
 constexpr uint32_t GROUP_SYMS = UNIT_SYMS * GROUP_UNITS;            // 16,384
 constexpr int BITS_THREADS = 512;
-constexpr int E2_WARPS = 24;
+#ifndef HF_E2_WARPS
+#define HF_E2_WARPS 20
+#endif
+constexpr int E2_WARPS = HF_E2_WARPS;
 constexpr int E2_THREADS = E2_WARPS * 32;
 constexpr uint32_t E2_PLANE_BYTES = NSYM * 3;                       // p16 + p8
 constexpr uint32_t E2_WIN = 372;                                    // staging words per warp (multiple of 4)
@@ -387,33 +390,35 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
 
         uint4 cur0 = make_uint4(0, 0, 0, 0), cur1 = cur0;       // my 16 symbols of the unit at hand (when have_cur)
         bool have_cur = false;
-        for (uint32_t u = 0; u < GROUP_UNITS; u++) {
-            const uint64_t unit = g * GROUP_UNITS + u;
-            if (unit >= nunits) break;
+        // 32-bit bounds for the unit loop (64-bit unit numbers in it cost registers the kernel does not have):
+        // units of this group, units whose successor is whole too, my lane's symbols of the group's first unit
+        const uint64_t unit0 = g * GROUP_UNITS;
+        const uint32_t nu = (uint32_t)min((uint64_t)GROUP_UNITS, nunits - unit0);
+        const uint64_t whole = n_sym / UNIT_SYMS;               // whole units of the input
+        const uint32_t fast_end = whole > unit0 + 1 ? (uint32_t)min((uint64_t)GROUP_UNITS, whole - 1 - unit0) : 0u;
+        const uint8_t *gin = in_bytes + (unit0 * UNIT_SYMS + lane * 16) * 2;
+        const bool first_group = g == 0;
+        uint32_t slow = 0;                                      // units of the group that take the general path
+        for (uint32_t u = 0; u < nu; u++) {
             const uint32_t bits = __shfl_sync(0xFFFFFFFFu, ub, u);
             const unsigned long long gbit = gstart + __shfl_sync(0xFFFFFFFFu, ux, u);  // unit's first bit, frame coordinates
             const uint32_t phase = (uint32_t)(gbit & 127);
             // words I own: those whose first bit is mine (the first unit also owns the word the stream starts in)
-            const uint32_t own_lo = unit == 0 ? (phase >> 5) : ((phase + 31) >> 5);
+            const bool first_unit = first_group && u == 0;
+            const uint32_t own_lo = first_unit ? (phase >> 5) : ((phase + 31) >> 5);
             const uint32_t end_rel = phase + bits;                  // window bit after my last bit
             const uint32_t own_hi = bits ? ((end_rel - 1) >> 5) : 0u;
             if (!(bits > 0 && own_hi >= own_lo)) { have_cur = false; continue; }   // my bits sit in a word the unit before me completes
 
             // the common case: whole units of an aligned input, this one and the next, away from the stream's ends
-            bool fast = aligned && unit != 0 && (unit + 2) * UNIT_SYMS <= n_sym && end_rel <= E2_WIN * 32;
+            bool fast = aligned && !first_unit && u < fast_end && end_rel <= E2_WIN * 32;
             uint32_t v[16];
             uint32_t L = 0;
-            uint4 nxt0 = cur0, nxt1 = cur1;
             uint32_t tail_sym = 0;
             if (fast) {
                 if (!have_cur) {
-                    const uint8_t *src = in_bytes + (unit * UNIT_SYMS + lane * 16) * 2;
+                    const uint8_t *src = gin + u * (UNIT_SYMS * 2);
                     cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
-                }
-                {   // the next unit's symbols: prefetched for the next step; its first 16, one per lane, complete my last word
-                    const uint8_t *src = in_bytes + ((unit + 1) * UNIT_SYMS + lane * 16) * 2;
-                    nxt0 = ld_stream_v4(src); nxt1 = ld_stream_v4(src + 16);
-                    tail_sym = reinterpret_cast<const uint16_t *>(in_bytes)[(unit + 1) * UNIT_SYMS + (lane & 15)];
                 }
                 const uint32_t w8[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
                 uint32_t zero = 0xFFFFFFFFu;
@@ -427,9 +432,16 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     L += 31 - __clz(x | 1u);
                 }
                 if (__any_sync(0xFFFFFFFFu, zero == 0)) fast = false;   // a code longer than 23 bits
+                if (fast) {
+                    // my symbols are codes now: their registers take the next unit's symbols, which arrive while this
+                    // unit is packed; the next unit's first 16, one per lane, complete my last word
+                    const uint8_t *src = gin + (u + 1) * (UNIT_SYMS * 2);
+                    cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
+                    tail_sym = *reinterpret_cast<const uint16_t *>(src - (int)(lane * 32) + (int)((lane & 15) * 2));
+                }
             }
-            if (!fast) {
-                encode_unit_general(C, unit, bits, gbit, lane);
+            if (!fast) {                                            // left for the loop below: a call in this loop makes
+                slow |= 1u << u;                                    // the compiler keep the loop's state in local memory
                 have_cur = false;
                 continue;
             }
@@ -483,7 +495,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     // the next unit is whole, so the word does fill up before the input ends
                     uint32_t have = have0, word = 0;
                     const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
-                    for (uint64_t sx = (unit + 1) * UNIT_SYMS; have < 32 && sx < n_sym; sx++) {
+                    for (uint64_t sx = (unit0 + u + 1) * UNIT_SYMS; have < 32 && sx < n_sym; sx++) {
                         uint32_t len;
                         unsigned long long code;
                         lookup_any(p16, p8, cb, in16[sx], len, code);
@@ -513,8 +525,14 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 }
             }
             __syncwarp();                                           // the window is reused
-            cur0 = nxt0; cur1 = nxt1;
             have_cur = true;
+        }
+        while (slow) {                                          // units are independent of each other: any order will do
+            const uint32_t u = __ffs(slow) - 1;
+            slow &= slow - 1;
+            const uint32_t bits = __shfl_sync(0xFFFFFFFFu, ub, u);
+            const unsigned long long gbit = gstart + __shfl_sync(0xFFFFFFFFu, ux, u);
+            encode_unit_general(C, unit0 + u, bits, gbit, lane);
         }
     }
 }
