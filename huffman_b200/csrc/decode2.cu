@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                   unsigned long long c0, unsigned long long c1, unsigned long long n_symbols,
-                  uint16_t *__restrict__ out, uint32_t check)
+                  uint16_t *__restrict__ out, uint32_t check, uint32_t upw)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
@@ -624,44 +624,56 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t bad = 0;
     constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
-    const unsigned long long nunits = c1 * UPC;     // units of the chunks [c0, c1)
-
-    for (unsigned long long ug = c0 * UPC + (unsigned long long)blockIdx.x * W3_WARPS + wid; ug < nunits;
-         ug += (unsigned long long)gridDim.x * W3_WARPS) {
-        const unsigned long long c = ug / UPC;
-        const uint32_t u = (uint32_t)(ug % UPC);
+    // A warp takes a RUN of upw consecutive units of one chunk (upw = 16, a whole chunk, on large streams; fewer on
+    // small ones so that every SM has work): the output offset is derived once per run and carried from unit to
+    // unit, and the next unit's record and payload words are loaded while the current one is walked.
+    const unsigned long long nruns = (c1 - c0) * (UPC / upw);
+    for (unsigned long long run = (unsigned long long)blockIdx.x * W3_WARPS + wid; run < nruns;
+         run += (unsigned long long)gridDim.x * W3_WARPS) {
+        const unsigned long long ug0 = c0 * UPC + run * upw;
+        const unsigned long long c = ug0 / UPC;
+        const uint32_t u0 = (uint32_t)(ug0 % UPC);
         const unsigned long long cbase = L.chunkBase[c];
         if (cbase >= n_symbols) continue;
-        // symbols of the chunk before my unit: lane l sums the 16 records [16 l, 16 l + 16) of the chunk
-        uint32_t before;
-        {
+        uint32_t ninf = L.info[c * DEC_THREADS + 32 * u0 + lane];
+        uint32_t nr[9];
+        load_sub(nr, frame, frame_bytes, c, 32 * u0 + lane, lane);
+        // symbols of the chunk before my run: lane l sums the 16 records [16 l, 16 l + 16) of the chunk
+        unsigned long long base = cbase;
+        if (u0) {
             const uint4 *ip = reinterpret_cast<const uint4 *>(L.info + c * DEC_THREADS);
             const uint4 a = ip[2 * lane], d = ip[2 * lane + 1];
             const uint32_t w8[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
             uint32_t sum = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) sum += ((w8[i] & 0xFFFFu) >> 6) + (w8[i] >> 22);
-            uint32_t x = (lane < 2 * u) ? sum : 0u;
+            uint32_t x = (lane < 2 * u0) ? sum : 0u;
 #pragma unroll
             for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-            before = x;
+            base += x;
         }
+        for (uint32_t u = u0; u < u0 + upw; u++) {
         const uint32_t t = 32 * u + lane;               // my subsequence of the chunk
-        const uint32_t inf = L.info[c * DEC_THREADS + t];
+        const uint32_t inf = ninf;
+        uint32_t r[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) r[i] = nr[i];
+        if (u + 1 < u0 + upw) {                         // the next unit of the run: in flight during this one's walk
+            ninf = L.info[c * DEC_THREADS + t + 32];
+            load_sub(nr, frame, frame_bytes, c, t + 32, lane);
+        }
         const uint32_t cnt = inf >> 6;
         uint32_t pos = (c == 0 && t == 0) ? (uint32_t)F0 : (inf & 63u);     // the stream head may sit past bit 63
         uint32_t x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
         const uint32_t off = x - cnt;                   // unit-relative index of my first symbol
-        unsigned long long total = __shfl_sync(0xFFFFFFFFu, x, 31);
-        const unsigned long long base = cbase + before;
-        if (base >= n_symbols) continue;
+        const uint32_t unit_total = __shfl_sync(0xFFFFFFFFu, x, 31);
+        unsigned long long total = unit_total;
+        if (base >= n_symbols) break;
         if (base + total > n_symbols) total = n_symbols - base;   // garbage past the payload end is dropped
         const uint32_t my_end = (uint32_t)min((unsigned long long)(off + cnt), total);
         uint32_t o = off;                               // unit-relative index of my next symbol
-        uint32_t r[9];
-        load_sub(r, frame, frame_bytes, c, t, lane);
 
         const uint32_t mis = (uint32_t)(base & 7);      // staging slot j <-> output symbol base - mis + j
         for (uint32_t w0 = 0; w0 < (uint32_t)total; w0 += W3_WIN) {
@@ -739,6 +751,8 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             }
             const bool last = base + off + cnt == n_symbols;        // my last code word is the stream's last: no successor
             if (cnt && my_end == off + cnt && !last && ((nxt >> 6) == 0 || pos < SUB_BITS || pos - SUB_BITS != (nxt & 63u))) bad = 1;
+        }
+        base += unit_total;
         }
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
@@ -1008,10 +1022,15 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
         HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         c->smem_attr[ATTR_WRITE] = true;
     }
-    unsigned long long grid = ((c1 - c0) * (DEC_THREADS / 32) + W3_WARPS - 1) / W3_WARPS;
+    // units per run: a whole chunk per warp when that still gives every warp of the machine 16 runs or more (fewer
+    // runs per warp leave the warps that got one less idle at the end)
+    uint32_t upw = DEC_THREADS / 32;
+    while (upw > 1 && (c1 - c0) * ((DEC_THREADS / 32) / upw) < 16ull * c->sm_count * W3_WARPS) upw >>= 1;
+    const unsigned long long nruns = (c1 - c0) * ((DEC_THREADS / 32) / upw);
+    unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
