@@ -32,6 +32,11 @@ namespace hf {
 
 constexpr uint32_t MICRO_D = 4;                                 // depth of a micro tree
 constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code resolved in shared memory (18)
+// t14 entry of a micro tree: base << 16 | MICRO_FLAG | starts of slots 1..15 (bit j - 1 = a leaf starts at slot j;
+// slot 0 always starts one).  A short code's entry, sym << 16 | len << 1, never has bit 15 set.
+constexpr uint32_t MICRO_FLAG = 0x8000u;
+__host__ __device__ __forceinline__ uint32_t micro_starts(uint32_t e) { return ((e & 0x7FFFu) << 1) | 1u; }
+__device__ __forceinline__ uint32_t micro_leaves(uint32_t e) { return __popc(e & 0x7FFFu) + 1u; }
 #ifndef W3_WARPS
 #define W3_WARPS 24                                             // warps of the write kernel's CTA
 #endif
@@ -83,7 +88,7 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
                 if ((j & ((1u << (MICRO_MAX - len)) - 1u)) == 0) mask |= 1u << j;       // first slot of its leaf
                 depths |= (len - MICRO_K - 1u) << (2 * j);
             }
-            if (ok) { entry = mask; dw = depths; }      // the base comes from dt_micro_kernel
+            if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; }      // the base comes from dt_micro_kernel
         }
         tab->t14[i] = entry;
         tab->d14[i] = dw;
@@ -111,7 +116,7 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
         v[j] = ent[j];
         const uint32_t e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (e4[k] & 1u) sum += __popc(e4[k] & 0xFFFFu);
+        for (int k = 0; k < 4; k++) if (e4[k] & MICRO_FLAG) sum += micro_leaves(e4[k]);
     }
     uint32_t x = sum;
 #pragma unroll
@@ -132,9 +137,9 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
         uint32_t e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (!(e4[k] & 1u)) continue;
-            const uint32_t mask = e4[k] & 0xFFFFu, n = __popc(mask);
-            e4[k] = base + n > NSYM ? 0u : ((base << 16) | mask);       // cannot overflow for a prefix code
+            if (!(e4[k] & MICRO_FLAG)) continue;
+            const uint32_t shape = e4[k] & 0xFFFFu, n = micro_leaves(shape);
+            e4[k] = base + n > NSYM ? 0u : ((base << 16) | shape);      // cannot overflow for a prefix code
             base += n;
         }
         ent[j] = make_uint4(e4[0], e4[1], e4[2], e4[3]);
@@ -147,9 +152,9 @@ __global__ void dt_leaves_kernel(DecodeTable *__restrict__ tab)
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (1u << MICRO_K)) return;
     const uint32_t e = tab->t14[p];
-    if (!(e & 1u)) return;
+    if (!(e & MICRO_FLAG)) return;
     uint32_t base = e >> 16;
-    for (uint32_t m = e & 0xFFFFu; m; m &= m - 1)
+    for (uint32_t m = micro_starts(e); m; m &= m - 1)
         tab->leaves[base++] = tab->micro_sym[p * (1u << MICRO_D) + (__ffs(m) - 1)];
 }
 
@@ -164,19 +169,25 @@ int launch_table_planes(Ctx *c, DecodeTable *d_tab)
     return HF_OK;
 }
 
-// length of the code word at the head of `win` from a micro-tree entry e (bit 0 set); b = slot of the next 4 bits
-__device__ __forceinline__ uint32_t micro_len(uint32_t e, uint32_t b)
+__device__ __forceinline__ uint32_t msb(uint32_t x)              // position of the highest set bit (x != 0)
 {
-    const uint32_t low = (2u << b) - 1u;                        // slots 0 .. b
-    const uint32_t m = e & 0xFFFFu;
-    const uint32_t s = 31u - __clz(m & low);                    // slot where the leaf that holds b starts
-    const uint32_t nx = __ffs((m | 0x10000u) & ~low) - 1u;      // slot where the next leaf starts (16 = none)
-    return __clz(nx - s) - (31u - MICRO_MAX);                   // MICRO_MAX - log2(leaf slots)
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
 }
-__device__ __forceinline__ uint32_t micro_slot(uint32_t win) { return (win >> (32 - MICRO_MAX)) & ((1u << MICRO_D) - 1u); }
-__device__ __forceinline__ uint32_t micro_leaf(uint32_t e, uint32_t b)
+
+// Code word at the head of `win` from a micro-tree entry e: its length and the index of its leaf.  b = the 4 bits
+// after the 14-bit prefix.  Starts at or below b, moved to the top of a word: the distance down to the leaf's start is
+// a count of leading zeros, its rank a population count; the starts above b, bit-reversed and moved to the top, give
+// the distance up to the next leaf the same way (the flag bit is the start of "slot 16").
+__device__ __forceinline__ void micro_decode(uint32_t e, uint32_t win, uint32_t &len, uint32_t &leaf)
 {
-    return (e >> 16) + __popc(e & 0xFFFFu & ((2u << b) - 1u)) - 1u;
+    const uint32_t b = (win >> (32 - MICRO_MAX)) & ((1u << MICRO_D) - 1u);
+    const uint32_t below = ((e << 1) | 1u) << (31u - b);        // slot b at bit 31, slot 0 (always a start) at 31 - b
+    const uint32_t above = __brev(e) << b;                      // slot b + 1 at bit 31
+    const uint32_t slots = 63u - msb(below) - msb(above);       // clz + clz + 1: slots of the leaf, 1, 2, 4 or 8
+    len = MICRO_MAX - msb(slots);
+    leaf = (e >> 16) + __popc(below) - 1u;
 }
 
 // ---- the rare way: any code length, bits straight from global memory ----------------------------
@@ -695,10 +706,10 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         const uint32_t win = __funnelshift_l(lo, hi, pos);
                         const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
                         uint32_t len, sym;
-                        if (e14 & 1u) {
-                            const uint32_t b = micro_slot(win);
-                            len = micro_len(e14, b);
-                            sym = s_leaves[micro_leaf(e14, b)];
+                        if (e14 & MICRO_FLAG) {
+                            uint32_t leaf;
+                            micro_decode(e14, win, len, leaf);
+                            sym = s_leaves[leaf];
                         } else {
                             len = (e14 >> 1) & 0x7Fu;
                             sym = e14 >> 16;
@@ -839,8 +850,9 @@ __device__ __forceinline__ void sub_count(const DecodeTable *tab, const uint8_t 
             const uint32_t win = __funnelshift_l(r[w + 1], r[w], pos);
             const uint32_t e14 = __ldg(tab->t14 + (win >> (32 - MICRO_K)));
             uint32_t len;
-            if (e14 & 1u) {
-                len = micro_len(e14, micro_slot(win));
+            if (e14 & MICRO_FLAG) {
+                uint32_t leaf;
+                micro_decode(e14, win, len, leaf);
             } else {
                 len = (e14 >> 1) & 0x7Fu;
                 if (len == 0) {
