@@ -88,6 +88,12 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
                 if ((j & ((1u << (MICRO_MAX - len)) - 1u)) == 0) mask |= 1u << j;       // first slot of its leaf
                 depths |= (len - MICRO_K - 1u) << (2 * j);
             }
+            // the two planes must tell the same lengths: every leaf an aligned block of slots of one depth.  A prefix
+            // code always is; a damaged table that is not goes to the flat planes, which both kernels read alike.
+            for (uint32_t j = 0; ok && j < (1u << MICRO_D); j++) {
+                const uint32_t d = (depths >> (2 * j)) & 3u, first = j & ~((8u >> d) - 1u);
+                if (((depths >> (2 * first)) & 3u) != d) ok = false;
+            }
             if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; }      // the base comes from dt_micro_kernel
         }
         tab->t14[i] = entry;
