@@ -225,22 +225,26 @@ __device__ __noinline__ uint32_t slow_decode(const DecodeTable *tab, const uint8
 }
 
 // ---- a thread's subsequence in registers (write kernel) ------------------------------------------
-// r[0..7]: the 8 big-endian words of subsequence (c, t); r[8]: the first word of the next one
-__device__ __forceinline__ void load_sub(uint32_t (&r)[9], const uint8_t *frame, unsigned long long frame_bytes,
-                                         unsigned long long c, uint32_t t, uint32_t lane)
+// r[0..7]: the 8 big-endian words of subsequence (c, t); r[8]: the first word of the next one.  Loaded in two halves, for a
+// prefetch: the loads now (nothing waits on them), the byte swaps and the neighbour's
+// first word when the subsequence is walked.  raw[0..7]: the 8 words as loaded; raw[8]: lane 31's look-ahead word
+__device__ __forceinline__ void load_sub_raw(uint32_t (&raw)[9], const uint8_t *frame, unsigned long long frame_bytes,
+                                             unsigned long long c, uint32_t t, uint32_t lane)
 {
     const unsigned long long b = c * (CHUNK_BITS / 8) + (unsigned long long)t * (SUB_BITS / 8);
     uint4 a = make_uint4(0, 0, 0, 0), d = make_uint4(0, 0, 0, 0);
     if (b < frame_bytes) a = __ldg(reinterpret_cast<const uint4 *>(frame + b));          // the frame is 16-byte aligned
     if (b + 16 < frame_bytes) d = __ldg(reinterpret_cast<const uint4 *>(frame + b + 16));
-    r[0] = bswap32(a.x); r[1] = bswap32(a.y); r[2] = bswap32(a.z); r[3] = bswap32(a.w);
-    r[4] = bswap32(d.x); r[5] = bswap32(d.y); r[6] = bswap32(d.z); r[7] = bswap32(d.w);
-    uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, r[0], 1);
-    if (lane == 31) {
-        nx = 0;
-        if (b + 32 < frame_bytes) nx = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b + 32)));
-    }
-    r[8] = nx;
+    raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = d.x; raw[5] = d.y; raw[6] = d.z; raw[7] = d.w;
+    raw[8] = 0;
+    if (lane == 31 && b + 32 < frame_bytes) raw[8] = __ldg(reinterpret_cast<const uint32_t *>(frame + b + 32));
+}
+__device__ __forceinline__ void finish_sub(uint32_t (&r)[9], const uint32_t (&raw)[9], uint32_t lane)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = bswap32(raw[i]);
+    const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, r[0], 1);
+    r[8] = lane == 31 ? bswap32(raw[8]) : nx;
 }
 
 // ---- synchronisation kernel ---------------------------------------------------------------------
@@ -654,7 +658,7 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
         if (cbase >= n_symbols) continue;
         uint32_t ninf = L.info[c * DEC_THREADS + 32 * u0 + lane];
         uint32_t nr[9];
-        load_sub(nr, frame, frame_bytes, c, 32 * u0 + lane, lane);
+        load_sub_raw(nr, frame, frame_bytes, c, 32 * u0 + lane, lane);
         // symbols of the chunk before my run: lane l sums the 16 records [16 l, 16 l + 16) of the chunk
         unsigned long long base = cbase;
         if (u0) {
@@ -673,11 +677,10 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
         const uint32_t t = 32 * u + lane;               // my subsequence of the chunk
         const uint32_t inf = ninf;
         uint32_t r[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) r[i] = nr[i];
+        finish_sub(r, nr, lane);
         if (u + 1 < u0 + upw) {                         // the next unit of the run: in flight during this one's walk
             ninf = L.info[c * DEC_THREADS + t + 32];
-            load_sub(nr, frame, frame_bytes, c, t + 32, lane);
+            load_sub_raw(nr, frame, frame_bytes, c, t + 32, lane);
         }
         const uint32_t cnt = inf >> 6;
         uint32_t pos = (c == 0 && t == 0) ? (uint32_t)F0 : (inf & 63u);     // the stream head may sit past bit 63
