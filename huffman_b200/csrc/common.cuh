@@ -79,10 +79,11 @@ struct DecodeTable {
     LongCode longs[NSYM];
     // planes of the word-walk kernels (decode2.cu), derived from t1 / t2 by the dt_planes / dt_micro kernels
     //   t14     by the next 14 bits, in shared memory:
-    //             (sym << 16) | (len << 1)   a code of at most 14 bits (bit 0 clear, len >= 1)
-    //             (base << 16) | mask        every code below this prefix has 15..18 bits (a complete "micro tree" of
-    //                                        depth <= 4): mask bit j = a leaf starts at slot j of the next 4 bits
-    //                                        (bit 0 always set), its symbols are leaves[base ...] in code order
+    //             (sym << 16) | (len << 1)   a code of at most 14 bits (bit 15 clear, len >= 1)
+    //             (base << 16) | 0x8000 | starts   every code below this prefix has 15..18 bits (a complete "micro
+    //                                        tree" of depth <= 4): starts bit j - 1 = a leaf starts at slot j of the next
+    //                                        4 bits (slot 0 always starts one; bit 15 marks the entry), its symbols are
+    //                                        leaves[base ...] in code order
     //             0                          deeper, incomplete or absent: take the flat planes
     //   leaves  symbols of the micro trees, in shared memory of the write kernel
     //   lenflat / flat2   length / (sym << 8) | len by the next k2 bits (<= k2 <= 22), L2 resident

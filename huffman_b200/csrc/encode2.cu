@@ -8,7 +8,7 @@
 //   enc_bits_kernel     bits of every unit (u32) and of every group, from the 64 KiB length plane in shared
 //                       memory.  Reads N, writes N / 256.
 //   enc_scan*_kernel    exclusive scan of the group totals (two tiny launches).
-//   encode2_kernel      one persistent CTA per SM, 24 warps, the 192 KiB code table (24-bit entries in two planes,
+//   encode2_kernel      one persistent CTA per SM, 20 warps, the 192 KiB code table (24-bit entries in two planes,
 //                       index XOR-folded against bank conflicts) in shared memory.  Every WARP packs groups on its
 //                       own: unit start = group start + a shuffle scan of the 32 unit counts; the lanes look their
 //                       16 codes up, a shuffle scan of the lane totals gives the lane's bit offset, pairs of codes
