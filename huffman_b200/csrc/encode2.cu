@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t fold16(uint32_t sym) { return sym ^ (sym >> 
 __device__ __forceinline__ uint32_t lds8(uint32_t a)
 {
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));        // tables that do not change after the CTA's barrier
     return v;
 }
 
@@ -95,13 +95,35 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
     const uint64_t nwarps = (uint64_t)gridDim.x * (BITS_THREADS / 32);
     for (uint64_t g = warp0; g < ngroups; g += nwarps) {
         uint32_t mine = 0;
+        if (aligned && (g + 1) * GROUP_SYMS <= n_sym) {
+            // a whole group of an aligned input: the next unit's symbols are loaded while this one's lengths are
+            // looked up, and there is no per-symbol end test (a predicated lookup makes the compiler rebuild the
+            // shared base address for every symbol)
+            const uint8_t *src = in_bytes + (g * GROUP_SYMS + lane * 16) * 2;
+            uint4 a = ld_stream_v4(src), b = ld_stream_v4(src + 16);
 #pragma unroll 4
+            for (uint32_t u = 0; u < GROUP_UNITS; u++) {
+                uint4 na = a, nb = b;
+                if (u + 1 < GROUP_UNITS) { na = ld_stream_v4(src + (u + 1) * (UNIT_SYMS * 2)); nb = ld_stream_v4(src + (u + 1) * (UNIT_SYMS * 2) + 16); }
+                const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t t = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) t += lds8(len_a + fold16(w8[i] & 0xFFFFu)) + lds8(len_a + fold16(w8[i] >> 16));
+                t = __reduce_add_sync(0xFFFFFFFFu, t);
+                if (lane == u) mine = t;
+                a = na; b = nb;
+            }
+            W.unit_bits[g * GROUP_UNITS + lane] = mine;
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, mine);
+            if (lane == 0) W.group_bits[g] = tot;
+            continue;
+        }
         for (uint32_t u = 0; u < GROUP_UNITS; u++) {
             const uint64_t unit = g * GROUP_UNITS + u;
             uint32_t t = 0;
-            if ((unit + 1) * UNIT_SYMS <= n_sym) {              // a whole unit: no per-symbol end test (a predicated
-                uint32_t sym[16];                               // lookup makes the compiler rebuild the shared base
-                load_unit(in_bytes, n_sym, aligned, unit, lane, sym);       // address for every symbol)
+            if ((unit + 1) * UNIT_SYMS <= n_sym) {
+                uint32_t sym[16];
+                load_unit(in_bytes, n_sym, aligned, unit, lane, sym);
 #pragma unroll
                 for (int j = 0; j < 16; j++) t += lds8(len_a + fold16(sym[j]));
                 t = __reduce_add_sync(0xFFFFFFFFu, t);
