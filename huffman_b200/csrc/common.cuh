@@ -91,9 +91,10 @@ struct DecodeTable {
     uint32_t pad2[3];
     alignas(16) uint32_t t14[1u << MICRO_K];
     alignas(16) uint16_t leaves[NSYM];
-    // d14: what the synchronisation walks need of t14 (lengths only): (len << 4) | 0xC for a code of at most 14 bits
-    // (0xC alone: not here), else the micro tree as 16 two-bit fields, field j = (length at slot j) - 15.  A micro tree
-    // never has the low nibble 0xC: slot 0 at depth 1 covers slot 1 as well.
+    // d14: what the synchronisation walks need of t14 (lengths only).  A code of at most 14 bits:
+    // (len << 28) | (n << 8) | (bits << 4) | 0xC, n = code words these 14 bits hold completely and their total bits
+    // (0x10C: not here, take the flat planes).  Else the micro tree as 16 two-bit fields, field j = (length at slot j)
+    // - 15; a micro tree never has the low nibble 0xC: slot 0 at depth 1 covers slot 1 as well.
     alignas(16) uint32_t d14[1u << MICRO_K];
     alignas(16) uint16_t micro_sym[16u << MICRO_K];     // build scratch: symbol at every slot of every prefix
     alignas(16) uint8_t lenflat[1u << FLAT_MAX];

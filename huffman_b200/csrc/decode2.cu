@@ -73,10 +73,19 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
         // entry of the 14-bit prefix i: a short code, or the shape of the micro tree below it
         const uint32_t w0 = i << (32 - MICRO_K);
         const uint32_t e0 = lookup_win32(tab, w0);
-        uint32_t entry = 0, dw = 0xCu;
+        uint32_t entry = 0, dw = 0x10Cu;                  // not here: no bits, counted as one code word by the flat path
         if (e0 && (e0 & 0x7Fu) <= MICRO_K) {
             entry = ((e0 >> 8) << 16) | ((e0 & 0x7Fu) << 1);
-            dw = ((e0 & 0x7Fu) << 4) | 0xCu;
+            // the lengths-only twin also says how many code words these 14 bits hold completely, and their bits
+            uint32_t tot = e0 & 0x7Fu, cnt = 1;
+            for (;;) {
+                const uint32_t e = lookup_win32(tab, w0 << tot);
+                const uint32_t len = e & 0x7Fu;
+                if (e == 0 || len == 0 || tot + len > MICRO_K) break;
+                tot += len;
+                cnt++;
+            }
+            dw = ((e0 & 0x7Fu) << 28) | (cnt << 8) | (tot << 4) | 0xCu;
         } else {
             uint32_t mask = 0, depths = 0;
             bool ok = true;
@@ -289,7 +298,7 @@ constexpr uint32_t CHK_NONE = 0xFFFFFFFFu;
 
 // Walks the code words of a span from bit `start` to `lim`.  RESYNC: `rec` describes an earlier walk; stop at
 // the first checkpoint both walks share and keep the earlier record from there on (`end` stays the earlier one's).
-template <bool RESYNC>
+template <bool RESYNC, bool MULTI>
 __device__ __forceinline__ void walk_span(const uint32_t *row, uint32_t t14_a, const DecodeTable *tab,
                                           const uint8_t *frame, unsigned long long frame_bytes,
                                           unsigned long long span_bit0, uint32_t k2shift, uint32_t start, uint32_t lim,
@@ -315,7 +324,12 @@ __device__ __forceinline__ void walk_span(const uint32_t *row, uint32_t t14_a, c
             const uint32_t win = __funnelshift_l(lds32(wa + 4), lds32(wa), pos);
             const uint32_t e14 = lds32(t14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));    // the d14 plane
             const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
-            uint32_t len = ((e14 & 0xFu) != 0xCu) ? deep : (e14 >> 4);
+            const bool micro = (e14 & 0xFu) != 0xCu;
+            uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
+            if (MULTI) {                            // all the code words the 14 bits hold, when they end inside the segment
+                const uint32_t tot = (e14 >> 4) & 0xFu;
+                if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
+            }
             if (len == 0) {
                 len = __ldg(tab->lenflat + (win >> k2shift));
                 if (len == 0) {
@@ -325,7 +339,7 @@ __device__ __forceinline__ void walk_span(const uint32_t *row, uint32_t t14_a, c
                 }
             }
             pos += len;
-            n++;
+            n += cnt;
         }
     }
     ncnt[1] |= n << 24;
@@ -378,8 +392,14 @@ struct SyncCtx {
 // One team converges on one group (GROUP_CHUNKS chunks): per-subsequence records, chunk totals and overflows.
 // exact: the group's first code word starts `start` bits into it (the stream head, or the true overflow of the group
 // before when a group is redone); otherwise the first span starts from a guess like every other one.
-__device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long grp, bool exact, uint32_t start, uint32_t &bad)
+// dense: code words my warp counted in the group before (0 at first).  Short code words come several to a 14-bit
+// look-up; when the warp's last 32 Kbit held more than DENSE_MIN of them (under ~10 bits each) the walks take all the
+// code words an entry holds in one step (walk_span<.., true>), which costs every step a few instructions more.
+constexpr uint32_t DENSE_MIN = 32u * SPAN_BITS / 10u;
+__device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long grp, bool exact, uint32_t start, uint32_t &bad,
+                                           uint32_t &dense)
 {
+    const bool multi = dense > DENSE_MIN;
     const uint8_t *frame = S.frame;
     const unsigned long long frame_bytes = S.frame_bytes, F0 = S.F0, range_end_bit = S.range_end_bit, nch = S.nch;
     const DecodeTable *tab = S.tab;
@@ -432,7 +452,11 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
         nwalk++;
     };
     if (lim) {
-        if (p < lim) { walk_span<false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad); memo_add(p, end); }
+        if (p < lim) {
+            if (multi) walk_span<false, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            else walk_span<false, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            memo_add(p, end);
+        }
         else end = p - lim;
         rec_end = end;
     }
@@ -460,7 +484,8 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
                     end = hit & 0xFFu;              // rec stays with the walk it describes
                 } else if (q < lim) {
                     end = rec_end;                  // a merge keeps the recorded walk's end
-                    walk_span<true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                    if (multi) walk_span<true, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
+                    else walk_span<true, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
                     rec_p = q; rec_end = end;
                     memo_add(q, end);
                 } else {
@@ -478,7 +503,8 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
     if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
         if (p < lim) {
             end = rec_end;
-            walk_span<true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            if (multi) walk_span<true, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
+            else walk_span<true, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
         } else {
             rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
         }
@@ -504,6 +530,7 @@ __device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long 
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     if (lane == 0) s_red[wid] = v;
+    dense = v;
     team_sync(team);
     constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
     const unsigned long long c = grp * GROUP_CHUNKS + tt / TPC;
@@ -543,9 +570,10 @@ dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     uint32_t bad = 0;
     __syncthreads();                                    // planes loaded
 
+    uint32_t dense = 0;
     for (unsigned long long grp = g_first + (unsigned long long)blockIdx.x * S3_TEAMS + team; grp < g_last;
          grp += (unsigned long long)gridDim.x * S3_TEAMS)
-        sync_group(S, grp, grp == 0 && !speculative, (uint32_t)F0, bad);
+        sync_group(S, grp, grp == 0 && !speculative, (uint32_t)F0, bad, dense);
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
@@ -582,6 +610,7 @@ dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_b
     __syncthreads();
 
     const unsigned long long g_lo = g_first ? g_first : 1;      // the first group of a stream has an exact start
+    uint32_t dense = 0;
     for (unsigned long long g = g_lo + (unsigned long long)blockIdx.x * S3_TEAMS + team; g < g_last;
          g += (unsigned long long)gridDim.x * S3_TEAMS) {
         // the head of a run: given up on, and the group before was not
@@ -589,7 +618,7 @@ dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_b
         if (g > g_lo && L.chunkE2[(g - 1) * GROUP_CHUNKS] == CHUNK_DIRTY) continue;
         for (unsigned long long cur = g;;) {
             const uint32_t s = L.chunkE[cur * GROUP_CHUNKS - 1];    // final: the group before is settled
-            sync_group(S, cur, true, s, bad);                       // also resets chunkE2 of its chunks
+            sync_group(S, cur, true, s, bad, dense);                // also resets chunkE2 of its chunks
             team_sync(team);                                        // the group's records are in global memory
             const unsigned long long next = cur + 1;
             if (next >= g_last) break;
