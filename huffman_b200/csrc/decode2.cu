@@ -13,18 +13,21 @@
 //     straight from global memory; the walk is unrolled over the words, so the 32-bit window of a code word
 //     is a funnel shift of two registers — no shared-memory staging of the payload, no bit reader;
 //   * the table of the hot loop is ONE 64 KiB shared-memory plane indexed by 14 bits whose entries are either a
-//     code word of at most 14 bits or a "micro tree": the shape (16-bit leaf-start mask) of the complete
+//     code word of at most 14 bits or a "micro tree": the shape (leaf-start bits) of the complete
 //     depth-4 subtree below that prefix, from which the length of a 15..18-bit code is a few bit operations and
 //     its symbol one more shared-memory load (leaves[base + rank], 128 KiB, write kernel only).  The 65,536
 //     byte pairs of a flat or mixed stream get 17/18-bit codes, so a plain direct table of that depth would
 //     need 1 MiB; here every code of up to 18 bits is resolved without leaving the SM.  Deeper or incomplete
 //     prefixes take ONE gather from a flat second-level plane (<= 22 bits, L2 resident); anything beyond goes
 //     through decode.cu's tables;
-//   * re-synchronisation is detected at four checkpoints per subsequence (the first code word boundary
-//     at or after bits 0/64/128/192, with the symbol count of every 64-bit segment), which costs two
-//     instructions per checkpoint instead of a 256-bit boundary mask maintained per symbol.
+//   * re-synchronisation is detected at checkpoints every 128 bits (the first code word boundary at or after
+//     the checkpoint, with the symbol count of every segment), which costs two instructions per checkpoint
+//     instead of a 256-bit boundary mask maintained per symbol;
+//   * what the per-source-line and per-SASS-instruction views of ncu found later is listed in profiles/README.md
+//     (shared-memory base addresses rebuilt inside loops, loop state in local memory around a call, loads that
+//     were waited for where they were issued, single-lane tails).
 //
-// Algorithmic bytes: dec_sync2 reads C; dec_write2 reads C and writes N.
+// Algorithmic bytes: dec_sync3 reads C; dec_write3 reads C and writes N.
 #include "common.cuh"
 #include "decode_common.cuh"
 
