@@ -18,7 +18,7 @@ namespace hf {
 
 constexpr int HIST_THREADS = 1024;
 constexpr int HIST_WORDS = 32768;           // packed u16 pairs
-constexpr int HIST_UNROLL = 4;              // 4 x 16 B in flight per thread
+constexpr int HIST_UNROLL = 2;              // 2 x 16 B counted while the next 2 x 16 B are in flight, per thread
 constexpr uint64_t HIST_SMALL_BYTES = 1u << 18;
 
 __device__ __forceinline__ uint32_t fold(uint32_t sym) { return sym ^ (sym >> 8); }   // involution on 16 bits
@@ -81,21 +81,36 @@ hist_smem_kernel(const uint4 *__restrict__ in, uint64_t n_vec, uint32_t *__restr
     const uint32_t lane = threadIdx.x & 31;         // whole warps only: count_vec uses warp-wide operations
     uint32_t skip = 0;                              // steps for which this warp does not try to aggregate
     uint32_t hot = 0x10000u;                        // the warp's candidate symbol (none yet)
-    for (; (i - lane) + 31 + (HIST_UNROLL - 1) * HIST_THREADS < n_vec; i += step) {
+    // software pipeline: HIST_UNROLL vectors are counted while the next HIST_UNROLL are in flight
+    auto whole = [&](uint64_t at) { return (at - lane) + 31 + (HIST_UNROLL - 1) * HIST_THREADS < n_vec; };
+    uint4 nv[HIST_UNROLL];
+    bool have = whole(i);
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < HIST_UNROLL; j++) nv[j] = ld_stream_v4(in + i + j * HIST_THREADS);
+    }
+    while (have) {
         uint4 v[HIST_UNROLL];
 #pragma unroll
-        for (int j = 0; j < HIST_UNROLL; j++) v[j] = ld_stream_v4(in + i + j * HIST_THREADS);
+        for (int j = 0; j < HIST_UNROLL; j++) v[j] = nv[j];
+        const bool more = whole(i + step);
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < HIST_UNROLL; j++) nv[j] = ld_stream_v4(in + i + step + j * HIST_THREADS);
+        }
         if (skip == 0) {
             if (hot > 0xFFFFu) hot = __shfl_sync(0xFFFFFFFFu, v[0].x & 0xFFFFu, 0);
             uint32_t hits = 0;
 #pragma unroll
             for (int j = 0; j < HIST_UNROLL; j++) hits += count_vec(sh, ghist, v[j], hot);
-            if (hits < HIST_UNROLL * 24) { skip = 15; hot = 0x10000u; }    // under ~10 % of the symbols: not worth it
+            if (hits < HIST_UNROLL * 24) { skip = 15 * (4 / HIST_UNROLL); hot = 0x10000u; }   // under ~10 % of the symbols: not worth it
         } else {
             skip--;
 #pragma unroll
             for (int j = 0; j < HIST_UNROLL; j++) count_vec_partial(sh, ghist, v[j]);
         }
+        i += step;
+        have = more;
     }
     for (; i < n_vec; i += HIST_THREADS)            // ragged end of this CTA's last strip, bin by bin
         count_vec_partial(sh, ghist, ld_stream_v4(in + i));
