@@ -55,7 +55,10 @@ static_assert(offsetof(Codebook, p8) == offsetof(Codebook, p16) + NSYM * 2, "enc
 constexpr uint32_t K1 = 12;
 constexpr uint32_t K2MAX = 12;
 constexpr uint32_t T2_CAP = 1u << 20;          // entries; 2^K1 prefixes x 2^8 always fits
-constexpr uint32_t FLAT_MAX = 22;              // index bits of the flat second-level planes
+#ifndef HF_FLAT_MAX
+#define HF_FLAT_MAX 22
+#endif
+constexpr uint32_t FLAT_MAX = HF_FLAT_MAX;     // index bits of the flat second-level planes
 constexpr uint32_t MICRO_K = 14;               // index bits of the shared-memory plane; micro trees add up to 4
 struct LongCode {
     unsigned long long code_left;               // left aligned in 64 bits
