@@ -28,6 +28,8 @@
 //     were waited for where they were issued, single-lane tails).
 //
 // Algorithmic bytes: dec_sync3 reads C; dec_write3 reads C and writes N.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "decode_common.cuh"
 
@@ -40,6 +42,49 @@ constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code 
 constexpr uint32_t MICRO_FLAG = 0x8000u;
 __host__ __device__ __forceinline__ uint32_t micro_starts(uint32_t e) { return ((e & 0x7FFFu) << 1) | 1u; }
 __device__ __forceinline__ uint32_t micro_leaves(uint32_t e) { return __popc(e & 0x7FFFu) + 1u; }
+// ---- micro-tree shapes (common.cuh) ----------------------------------------------------------------
+__device__ uint16_t g_shape_id[1u << 15];
+__device__ __align__(16) uint8_t g_shape_lut[SHAPE_LUT_BYTES];
+
+int shapes_upload(Ctx *c)
+{
+    static uint16_t h_id[1u << 15];
+    static uint8_t h_lut[SHAPE_LUT_BYTES];
+    static bool built = false;
+    if (!built) {
+        uint32_t n = 0;
+        for (uint32_t m15 = 0; m15 < (1u << 15); m15++) {
+            const uint32_t mask = (m15 << 1) | 1u;      // bit j: a leaf starts at slot j
+            bool valid = true;
+            for (uint32_t s0 = 0; s0 < 16 && valid;) {
+                uint32_t e = s0 + 1;
+                while (e < 16 && !((mask >> e) & 1u)) e++;
+                const uint32_t r = e - s0;               // slots of this leaf: 1, 2, 4 or 8, aligned
+                if (r == 16 || (r & (r - 1)) || (s0 & (r - 1))) valid = false;
+                s0 = e;
+            }
+            h_id[m15] = 0xFFFFu;
+            if (!valid || n >= SHAPE_COUNT) continue;
+            for (uint32_t b = 0; b < 16; b++) {
+                uint32_t s0 = b;
+                while (!((mask >> s0) & 1u)) s0--;
+                uint32_t e = s0 + 1;
+                while (e < 16 && !((mask >> e) & 1u)) e++;
+                uint32_t lg = 0;
+                while ((1u << lg) < e - s0) lg++;
+                const uint32_t rank = (uint32_t)__builtin_popcount(mask & ((2u << b) - 1u)) - 1u;
+                h_lut[n * 16 + b] = (uint8_t)((3u - lg) | ((2u * rank) << 2));
+            }
+            h_id[m15] = (uint16_t)n++;
+        }
+        if (n != SHAPE_COUNT) return set_err(c, HF_ERR_INTERNAL, "micro-tree shapes: %u, expected %u", n, SHAPE_COUNT);
+        built = true;
+    }
+    HF_CUDA(c, cudaMemcpyToSymbol(g_shape_id, h_id, sizeof(h_id)));
+    HF_CUDA(c, cudaMemcpyToSymbol(g_shape_lut, h_lut, sizeof(h_lut)));
+    return HF_OK;
+}
+
 #ifndef W3_WARPS
 #define W3_WARPS 24                                             // warps of the write kernel's CTA
 #endif
@@ -50,6 +95,10 @@ constexpr int W3_THREADS = W3_WARPS * 32;
 // output staging window of one warp (symbols, multiple of 8): what is left of the SM's 227 KiB beside the planes
 constexpr uint32_t W3_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - 64u) / W3_WARPS) / 2 - 8) & ~7u;
 constexpr size_t W3_SMEM = (4u << MICRO_K) + NSYM * 2 + (size_t)W3_WARPS * (W3_WIN + 8) * 2;
+// the same with the shape table (SHAPE_LUT_PAD bytes) between the planes and the windows
+constexpr uint32_t SHAPE_LUT_PAD = (SHAPE_LUT_BYTES + 63u) & ~63u;
+constexpr uint32_t W3L_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - SHAPE_LUT_PAD - 64u) / W3_WARPS) / 2 - 8) & ~7u;
+constexpr size_t W3L_SMEM = (4u << MICRO_K) + NSYM * 2 + SHAPE_LUT_PAD + (size_t)W3_WARPS * (W3L_WIN + 8) * 2;
 
 // ---- planes ------------------------------------------------------------------------------------
 // (sym << 8) | len of the code word that is a prefix of the left-aligned window, from t1 / t2; 0 when
@@ -76,7 +125,7 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
         // entry of the 14-bit prefix i: a short code, or the shape of the micro tree below it
         const uint32_t w0 = i << (32 - MICRO_K);
         const uint32_t e0 = lookup_win32(tab, w0);
-        uint32_t entry = 0, dw = 0x10Cu;                  // not here: no bits, counted as one code word by the flat path
+        uint32_t entry = 0, entry_s = 0, dw = 0x10Cu;     // not here: no bits, counted as one code word by the flat path
         if (e0 && (e0 & 0x7Fu) <= MICRO_K) {
             entry = ((e0 >> 8) << 16) | ((e0 & 0x7Fu) << 1);
             // the lengths-only twin also says how many code words these 14 bits hold completely, and their bits
@@ -106,9 +155,12 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
                 const uint32_t d = (depths >> (2 * j)) & 3u, first = j & ~((8u >> d) - 1u);
                 if (((depths >> (2 * first)) & 3u) != d) ok = false;
             }
-            if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; }      // the base comes from dt_micro_kernel
+            uint32_t sid = ok ? g_shape_id[mask >> 1] : 0xFFFFu;
+            if (sid == 0xFFFFu) ok = false;
+            if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; entry_s = (sid << 4) | MICRO_FLAG; }   // the base comes from dt_micro_kernel
         }
         tab->t14[i] = entry;
+        tab->t14s[i] = (entry & MICRO_FLAG) ? entry_s : entry;
         tab->d14[i] = dw;
     }
     if (i < (1u << k2)) {
@@ -128,6 +180,7 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
     constexpr uint32_t PER = (1u << MICRO_K) / 1024;    // 16 prefixes per thread
     uint4 v[PER / 4];
     uint4 *ent = reinterpret_cast<uint4 *>(tab->t14 + tid * PER);
+    uint32_t *ent_s = tab->t14s + tid * PER;
     uint32_t sum = 0;
 #pragma unroll
     for (uint32_t j = 0; j < PER / 4; j++) {
@@ -157,7 +210,9 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
         for (int k = 0; k < 4; k++) {
             if (!(e4[k] & MICRO_FLAG)) continue;
             const uint32_t shape = e4[k] & 0xFFFFu, n = micro_leaves(shape);
-            e4[k] = base + n > NSYM ? 0u : ((base << 16) | shape);      // cannot overflow for a prefix code
+            const bool fits = base + n <= NSYM;                         // cannot overflow for a prefix code
+            e4[k] = fits ? ((base << 16) | shape) : 0u;
+            ent_s[4 * j + k] = fits ? ((base << 16) | (ent_s[4 * j + k] & 0xFFFFu)) : 0u;
             base += n;
         }
         ent[j] = make_uint4(e4[0], e4[1], e4[2], e4[3]);
@@ -291,6 +346,19 @@ __device__ __forceinline__ uint32_t lds32(uint32_t shared_addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint32_t lds8s(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 
@@ -634,6 +702,305 @@ dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_b
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
+// -------------------------------------------------------------------------------------------------
+// dec_sync4_kernel: every WARP converges on one chunk by itself (no teams, no CTA or named barriers after the
+// table load).  A lane owns LANE_SUBS = 16 consecutive subsequences (512 bytes of payload): four times the span
+// of dec_sync3's threads, so a guessed start costs a quarter as many repeated walks per payload bit (a wrong
+// walk re-joins the true chain after tens of bits on skewed codes, after ~2,000 bits on the nearly fixed-length
+// codes of flat data).  The lane streams its span through a private shared-memory row, two subsequences (64
+// bytes, two whole sectors) at a time; the next pair is in flight in registers while this one is walked.  The
+// warp walks in lock step per subsequence (lanes wait for each other every 256 bits: ~21 code words), and the
+// per-subsequence records — which are also the output — are the checkpoints at which a repeated walk from a
+// corrected start recognises the earlier one.
+constexpr int S4_THREADS = 1024;
+constexpr int S4_WARPS = S4_THREADS / 32;
+constexpr uint32_t LANE_SUBS = DEC_THREADS / 32;                // 16
+constexpr uint32_t LANE_BITS = LANE_SUBS * SUB_BITS;            // 4096
+constexpr uint32_t ROW4_WORDS = SUB_BITS / 32 + 1;             // a subsequence + the word that follows it (odd: conflict-free)
+constexpr uint32_t REC4_WORDS = LANE_SUBS / 2 + 1;              // 16 u16 records + a pad word (odd)
+constexpr size_t S4_SMEM = (4u << MICRO_K) + (size_t)S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;
+static_assert(GROUP_CHUNKS == 1, "dec_sync4: a warp converges on one chunk");
+
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+struct Sync4Ctx {
+    const uint8_t *frame;
+    unsigned long long frame_bytes, F0, range_end_bit, nch;
+    const DecodeTable *tab;
+    DecWork *work;
+    uint32_t d14_a;                     // shared address of the d14 plane
+    uint32_t g, k2shift;
+};
+
+__device__ __forceinline__ uint32_t lane_limit(unsigned long long X, unsigned long long range_end_bit)
+{   // bits of the lane's span at frame bit X that lie before the end of the range (0 .. LANE_BITS)
+    if (X >= range_end_bit) return 0u;
+    const unsigned long long room = range_end_bit - X;
+    return room >= LANE_BITS ? LANE_BITS : (uint32_t)room;
+}
+
+// the 32 bytes of the frame at byte b (one sector) and the word after them, as loaded; zero past the end
+__device__ __forceinline__ void load_sub_raw4(uint4 &a, uint4 &d, uint32_t &next, const uint8_t *frame,
+                                              unsigned long long frame_bytes, unsigned long long b)
+{
+    a = make_uint4(0, 0, 0, 0); d = a; next = 0;
+    if (b < frame_bytes) a = ld_stream_v4(frame + b);
+    if (b + 16 < frame_bytes) d = ld_stream_v4(frame + b + 16);
+    if (b + 32 < frame_bytes) next = __ldg(reinterpret_cast<const uint32_t *>(frame + b + 32));
+}
+
+// The lanes with `live` set walk their spans from bit `wstart` (relative to the span) up to `lim`, writing one
+// record per subsequence into their record rows.  have_rec: the row describes an earlier walk of this span; the
+// new walk stops at the first subsequence it enters where the earlier one did and keeps the earlier records (and
+// the caller's `end`) from there on.  A walk that runs to `lim` sets end = overflow past it.
+template <bool MULTI>
+__device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uint32_t rec_a, unsigned long long span_bit0,
+                                          bool live, bool have_rec, uint32_t wstart, uint32_t lim, uint32_t &end, uint32_t &bad)
+{
+    const uint32_t d14_a = S.d14_a, k2shift = S.k2shift;
+    const unsigned long long span_byte0 = span_bit0 >> 3;
+    uint32_t pos = wstart;
+    uint4 na, nd;
+    uint32_t nnext = 0;
+    if (live) load_sub_raw4(na, nd, nnext, S.frame, S.frame_bytes, span_byte0);
+#pragma unroll 1
+    for (uint32_t k = 0; k < LANE_SUBS; k++) {
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        if (live) {
+            // my subsequence k: registers -> row (big-endian words); the next one goes in flight
+            sts32(row_a + 0, bswap32(na.x)); sts32(row_a + 4, bswap32(na.y)); sts32(row_a + 8, bswap32(na.z)); sts32(row_a + 12, bswap32(na.w));
+            sts32(row_a + 16, bswap32(nd.x)); sts32(row_a + 20, bswap32(nd.y)); sts32(row_a + 24, bswap32(nd.z)); sts32(row_a + 28, bswap32(nd.w));
+            sts32(row_a + 32, bswap32(nnext));
+            if (k + 1 < LANE_SUBS) load_sub_raw4(na, nd, nnext, S.frame, S.frame_bytes, span_byte0 + 32ull * (k + 1));
+            const uint32_t sub0 = SUB_BITS * k;
+            const uint32_t rel = pos - sub0;            // where this walk enters the subsequence (< 64 for codes <= 64 bits)
+            if (have_rec && pos < lim) {                // entering where the earlier walk did: the walks have met
+                const uint32_t old = lds16(rec_a + 2u * k);
+                if (old >= 64u && rel == (old & 63u)) live = false;
+            }
+            if (live) {
+                const uint32_t lw = min(lim, sub0 + SUB_BITS);
+                uint32_t n = 0;
+                while (pos < lw) {
+                    const uint32_t wa = row_a + ((pos >> 3) & 28u);
+                    const uint32_t win = __funnelshift_l(lds32(wa + 4), lds32(wa), pos);
+                    const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
+                    const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);
+                    const bool micro = (e14 & 0xFu) != 0xCu;
+                    uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
+                    if (MULTI) {                        // all the code words the 14 bits hold, when they end inside the subsequence
+                        const uint32_t tot = (e14 >> 4) & 0xFu;
+                        if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
+                    }
+                    if (len == 0) {
+                        len = __ldg(S.tab->lenflat + (win >> k2shift));
+                        if (len == 0) {
+                            const uint32_t e = slow_decode(S.tab, S.frame, S.frame_bytes, span_bit0 + pos);
+                            bad |= e >> 31;
+                            len = e & 0x7Fu;
+                        }
+                    }
+                    pos += len;
+                    n += cnt;
+                }
+                sts16(rec_a + 2u * k, n ? ((rel & 63u) | (n << 6)) : 0u);
+            }
+        }
+    }
+    if (live) end = pos - lim;          // ran to the limit (pos >= lim)
+}
+
+// One warp converges on chunk c.  exact: the chunk's first code word starts `start` bits into it (the stream head,
+// or the true overflow of the chunk before when a chunk is redone); otherwise lane 0 starts from a guess like every
+// other lane and dec_fix2_kernel repairs the chunk's first subsequences afterwards.  dense: code words this warp
+// counted in its last chunk (see DENSE_MIN).  mark: reset the chunk's repair mark (the regroup kernel must not).
+constexpr uint32_t DENSE4_MIN = CHUNK_BITS / 10u;
+template <bool MULTI>
+__device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, uint32_t rec_a, unsigned long long c,
+                                           bool exact, uint32_t start, bool mark, uint32_t &bad, uint32_t &dense)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    DecLayout L(S.work, S.nch);
+    const unsigned long long X = c * CHUNK_BITS + (unsigned long long)lane * LANE_BITS;
+    const uint32_t lim = lane_limit(X, S.range_end_bit);
+    const bool fixed = lane == 0;                       // lane 0 has no predecessor in the warp: exact start or guess
+    uint32_t p = (exact && lane == 0) ? start : (X >= S.F0 ? spec_start(X, S.F0, S.g) : 0u);
+    // `end`: overflow of the walk from p.  The record row describes the walk from rec_p, which ended at rec_end.
+    // memo: up to four (start + 1, end) pairs of walks of this span.  Data that does not re-synchronise (a long run
+    // of one code word is periodic) makes the fix-point hand a lane the same few starts again and again; a remembered
+    // start costs no walk, and the records of the final start are rebuilt once at the end.
+    uint32_t end = 0, rec_p = p, rec_end = 0, mslot = 0, nwalk = 0;
+    unsigned long long memo = 0;
+    bool have_rec = false;
+    const bool movable = !fixed && lim != 0;
+    // first pass: everybody walks
+    bool want = true, final = false;
+    uint32_t wstart = p;
+    for (;;) {
+        bool live = want && wstart < lim;
+        if (want && !live) {                            // starts at or past my limit: no code word of mine
+#pragma unroll
+            for (uint32_t k = 0; k < LANE_SUBS; k += 2) sts32(rec_a + 2u * k, 0u);
+            end = lim ? wstart - lim : 0u;
+            rec_p = wstart; rec_end = end; have_rec = false;
+        }
+        if (live) end = rec_end;                        // a walk that merges keeps the recorded walk's end
+        walk_lane<MULTI>(S, row_a, rec_a, X, live, have_rec, wstart, lim, end, bad);
+        if (live) {
+            rec_p = wstart; rec_end = end; have_rec = true;
+            memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((wstart + 1) << 8) | end) << (16 * mslot));
+            mslot = (mslot + 1) & 3;
+            nwalk++;
+        }
+        if (final) break;
+        // fix-point: my true start is my predecessor's overflow
+        for (;;) {
+            uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
+            want = movable && q != p;
+            uint32_t hit = 0;                           // ((q + 1) << 8) | end of a walk from q done before
+            if (want && nwalk >= 2) {                   // the first correction of a guess cannot be a repeat
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t en = (uint32_t)(memo >> (16 * i)) & 0xFFFFu;
+                    if ((en >> 8) == q + 1) hit = en;
+                }
+            }
+            if (want) { p = q; wstart = q; }
+            if (hit) { end = hit & 0xFFu; want = false; }       // the record row stays with the walk it describes
+            const bool any_want = __any_sync(0xFFFFFFFFu, want);
+            const bool any_hit = __any_sync(0xFFFFFFFFu, hit != 0);
+            if (any_want) break;                        // somebody walks
+            if (!any_hit) { final = true; break; }      // nothing moved: converged
+        }
+        if (final) {                                    // the final start was a remembered one: rebuild its records
+            want = lim != 0 && rec_p != p;
+            wstart = p;
+            if (!__any_sync(0xFFFFFFFFu, want)) break;
+        }
+    }
+
+    // ---- records out: 16 per lane, 32 contiguous bytes; chunk total and overflow ----
+    uint32_t r8[8], total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r8[i] = lds32(rec_a + 4u * i);
+        total += ((r8[i] & 0xFFFFu) >> 6) + (r8[i] >> 22);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(L.info + c * DEC_THREADS + lane * LANE_SUBS);
+    dst[0] = make_uint4(r8[0], r8[1], r8[2], r8[3]);
+    dst[1] = make_uint4(r8[4], r8[5], r8[6], r8[7]);
+    total = __reduce_add_sync(0xFFFFFFFFu, total);
+    dense = total;
+    if (lane == 0) {
+        L.chunkCnt[c] = total;
+        if (mark) L.chunkE2[c] = 0xFFFFFFFFu;
+    }
+    if (lane == 31) L.chunkE[c] = end;
+    // the lane whose span holds the end of the range reports the overflow past it
+    if (lim && lane_limit(X + LANE_BITS, S.range_end_bit) == 0) S.work->result[1] = end;
+}
+
+__device__ __forceinline__ void sync4_setup(uint32_t *smem, const DecodeTable *tab, uint32_t &d14_a, uint32_t &row_a, uint32_t &rec_a)
+{
+    const uint32_t tid = threadIdx.x;
+    const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);           // lengths only
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S4_THREADS) dst[i] = __ldg(src + i);
+    d14_a = opaque_shared_addr(smem);
+    row_a = d14_a + (4u << MICRO_K) + tid * (ROW4_WORDS * 4u);
+    rec_a = d14_a + (4u << MICRO_K) + S4_THREADS * (ROW4_WORDS * 4u) + tid * (REC4_WORDS * 4u);
+}
+
+__global__ void __launch_bounds__(S4_THREADS, 1)
+dec_sync4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                 unsigned long long nch, unsigned long long c_first, unsigned long long c_last, uint32_t speculative)
+{
+    extern __shared__ __align__(16) uint32_t s4_smem[];
+    if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
+    uint32_t d14_a, row_a, rec_a;
+    sync4_setup(s4_smem, tab, d14_a, row_a, rec_a);
+    const Sync4Ctx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, d14_a, speculative ? 1u : tab->len_gcd, 32u - tab->k2};
+    __syncthreads();                                    // plane loaded; the warps are on their own from here
+    const uint32_t wid = threadIdx.x >> 5;
+    uint32_t bad = 0, dense = 0;
+    for (unsigned long long c = c_first + (unsigned long long)blockIdx.x * S4_WARPS + wid; c < c_last;
+         c += (unsigned long long)gridDim.x * S4_WARPS) {
+        const bool exact = c == 0 && !speculative;
+        if (dense > DENSE4_MIN) sync_chunk<true>(S, row_a, rec_a, c, exact, (uint32_t)F0, true, bad, dense);
+        else sync_chunk<false>(S, row_a, rec_a, c, exact, (uint32_t)F0, true, bad, dense);
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// Chunks dec_fix2_kernel gave up on (marked CHUNK_DIRTY): the chain of the chunk before never meets the chain the
+// chunk recorded from its guessed start (data that does not re-synchronise, e.g. a long run of one code word).  The
+// marks are written before this kernel starts and never changed by it, so runs of marked chunks are disjoint and each
+// belongs to exactly one warp: the warp that finds a run's head redoes its chunks one after the other from their TRUE
+// starts, and walks on through unmarked chunks for as long as the overflow it hands over is not the start they
+// recorded — up to, not into, the next run's head.  All decisions are taken by lane 0 and broadcast.  What this leaves
+// open (a chain that reaches another run) is found by dec_verify_kernel and settled by the serial kernel.
+__global__ void __launch_bounds__(S4_THREADS, 1)
+dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+                    unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
+                    unsigned long long nch, unsigned long long c_first, unsigned long long c_last, uint32_t speculative)
+{
+    if (work->flags[3] == 0) return;                    // no chunk was given up on
+    extern __shared__ __align__(16) uint32_t s4_smem[];
+    if (tab->single_sym) return;
+    uint32_t d14_a, row_a, rec_a;
+    sync4_setup(s4_smem, tab, d14_a, row_a, rec_a);
+    const Sync4Ctx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, d14_a, speculative ? 1u : tab->len_gcd, 32u - tab->k2};
+    __syncthreads();
+    DecLayout L(work, nch);
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long c_lo = c_first ? c_first : 1;      // the first chunk of a stream has an exact start
+    uint32_t bad = 0, dense = 0;
+    for (unsigned long long c = c_lo + (unsigned long long)blockIdx.x * S4_WARPS + wid; c < c_last;
+         c += (unsigned long long)gridDim.x * S4_WARPS) {
+        uint32_t head = 0, s = 0;
+        if (lane == 0) {
+            head = L.chunkE2[c] == CHUNK_DIRTY && !(c > c_lo && L.chunkE2[c - 1] == CHUNK_DIRTY);
+            s = L.chunkE[c - 1];
+        }
+        head = __shfl_sync(0xFFFFFFFFu, head, 0);
+        if (!head) continue;
+        s = __shfl_sync(0xFFFFFFFFu, s, 0);
+        bool in_run = true;
+        for (unsigned long long cur = c;;) {
+            sync_chunk<false>(S, row_a, rec_a, cur, true, s, false, bad, dense);
+            const unsigned long long next = cur + 1;
+            if (next >= c_last) break;
+            uint32_t dirty = 0, first = 0, e = 0;
+            __syncwarp();
+            if (lane == 0) {
+                dirty = L.chunkE2[next] == CHUNK_DIRTY;
+                first = L.info[next * DEC_THREADS];
+                e = L.chunkE[cur];                      // written by lane 31 before the __syncwarp
+            }
+            dirty = __shfl_sync(0xFFFFFFFFu, dirty, 0);
+            first = __shfl_sync(0xFFFFFFFFu, first, 0);
+            e = __shfl_sync(0xFFFFFFFFu, e, 0);
+            if (dirty) {
+                if (!in_run) break;                     // another run's head: that run's warp takes it from there
+            } else {
+                in_run = false;
+                if (e == (first & 63u)) break;          // the chain meets what the next chunk recorded
+            }
+            s = e;
+            cur = next;
+        }
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
 // every group must start where the group before it ends; what the parallel repairs left open goes to the serial kernel
 __global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                                   unsigned long long g_first, unsigned long long g_last)
@@ -652,6 +1019,10 @@ __global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *
 // Every WARP works on its own: a unit of 32 consecutive subsequences (1 KiB of payload), whose output offset
 // it derives itself from the chunk's records (no CTA-wide scan, no CTA barrier after the planes are loaded).
 // The symbols of a unit are compacted in the warp's staging window and leave with aligned 128-bit stores.
+// LUT: the micro trees are decoded with the shape table (t14s + g_shape_lut: two dependent shared-memory loads and
+// nine ALU instructions for a 15..18-bit code) instead of bit arithmetic on the leaf starts (t14: eighteen, five of
+// them bit-find / bit-reverse / population counts).
+template <bool LUT>
 __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
@@ -659,21 +1030,30 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                   uint16_t *__restrict__ out, uint32_t check, uint32_t upw)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
+    constexpr uint32_t WIN = LUT ? W3L_WIN : W3_WIN;
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
     uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_leaves + NSYM);              // SHAPE_LUT_PAD (LUT only)
     if (tab->single_sym) return;
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint16_t *sout = s_leaves + NSYM + wid * (W3_WIN + 8);                      // this warp's window
+    uint16_t *sout = reinterpret_cast<uint16_t *>(s_lut + (LUT ? SHAPE_LUT_PAD : 0u)) + wid * (WIN + 8);   // this warp's window
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
+        const uint4 *src = reinterpret_cast<const uint4 *>(LUT ? tab->t14s : tab->t14);
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
         src = reinterpret_cast<const uint4 *>(tab->leaves);
         dst = reinterpret_cast<uint4 *>(s_leaves);
         for (uint32_t i = tid; i < NSYM * 2 / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
+        if (LUT) {
+            src = reinterpret_cast<const uint4 *>(g_shape_lut);
+            dst = reinterpret_cast<uint4 *>(s_lut);
+            for (uint32_t i = tid; i < SHAPE_LUT_BYTES / 16; i += W3_THREADS) dst[i] = src[i];
+        }
     }
     __syncthreads();
+    const uint32_t lut_a = opaque_shared_addr(s_lut);
+    const uint32_t leaves_a1 = lut_a - NSYM * 2 - 1u;               // (entry >> 15) = 2 * base + 1 for a micro entry
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t bad = 0;
     constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
@@ -728,8 +1108,8 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
         uint32_t o = off;                               // unit-relative index of my next symbol
 
         const uint32_t mis = (uint32_t)(base & 7);      // staging slot j <-> output symbol base - mis + j
-        for (uint32_t w0 = 0; w0 < (uint32_t)total; w0 += W3_WIN) {
-            const uint32_t wend = min((uint32_t)total, w0 + W3_WIN);
+        for (uint32_t w0 = 0; w0 < (uint32_t)total; w0 += WIN) {
+            const uint32_t wend = min((uint32_t)total, w0 + WIN);
             const uint32_t o_end = min(my_end, wend);
             if (o < o_end) {
                 uint16_t *sp = sout + (o - w0 + mis);
@@ -748,9 +1128,15 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
                         uint32_t len, sym;
                         if (e14 & MICRO_FLAG) {
-                            uint32_t leaf;
-                            micro_decode(e14, win, len, leaf);
-                            sym = s_leaves[leaf];
+                            if (LUT) {
+                                const uint32_t x = lds8s(lut_a + (e14 & 0x3FF0u) + ((win >> (32 - MICRO_MAX)) & 15u));
+                                len = (MICRO_K + 1) + (x & 3u);
+                                sym = lds16(leaves_a1 + (e14 >> 15) + (x >> 2));
+                            } else {
+                                uint32_t leaf;
+                                micro_decode(e14, win, len, leaf);
+                                sym = s_leaves[leaf];
+                            }
                         } else {
                             len = (e14 >> 1) & 0x7Fu;
                             sym = e14 >> 16;
@@ -1011,6 +1397,14 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
     work->flags[0] = 0;                                 // settled (the next slice starts clean)
 }
 
+// development switch (A/B timing): HF_SYNC=3 selects the team-based synchronisation kernels
+static bool use_sync3()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HF_SYNC"); v = (e && e[0] == '3') ? 1 : 0; }
+    return v == 1;
+}
+
 // chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
@@ -1025,9 +1419,17 @@ int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, un
     HF_LAUNCH_CHECK(c);
     unsigned long long grid = (ng + S3_TEAMS - 1) / S3_TEAMS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    HF_PROF(c, "dec_regroup_kernel");
-    dec_regroup_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
-    HF_LAUNCH_CHECK(c);
+    if (use_sync3()) {
+        HF_PROF(c, "dec_regroup_kernel");
+        dec_regroup_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
+        HF_LAUNCH_CHECK(c);
+    } else {
+        grid = (ng + S4_WARPS - 1) / S4_WARPS;
+        if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
+        HF_PROF(c, "dec_regroup4_kernel");
+        dec_regroup4_kernel<<<(unsigned)grid, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
+        HF_LAUNCH_CHECK(c);
+    }
     HF_PROF(c, "dec_verify_kernel"); dec_verify_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, c->stream>>>(d_tab, work, nch, g_first, g_last);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
@@ -1045,6 +1447,8 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
     if (!c->smem_attr[ATTR_SYNC]) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         HF_CUDA(c, cudaFuncSetAttribute(dec_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_sync4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_regroup4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM));
         c->smem_attr[ATTR_SYNC] = true;
     }
     unsigned long long ngroups = (nch + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
@@ -1056,6 +1460,15 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
         g_first = c0 / GROUP_CHUNKS;
         ngroups = (c1 + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
         if (ngroups <= g_first) return HF_OK;
+    }
+    if (!use_sync3()) {
+        unsigned long long grid4 = (ngroups - g_first + S4_WARPS - 1) / S4_WARPS;
+        if (grid4 > (unsigned long long)c->sm_count) grid4 = c->sm_count;
+        HF_PROF(c, "dec_sync4_kernel");
+        dec_sync4_kernel<<<(unsigned)grid4, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
+                                                                            g_first, ngroups, tail_only ? 1u : 0u);
+        HF_LAUNCH_CHECK(c);
+        return HF_OK;
     }
     unsigned long long grid = (ngroups - g_first + S3_TEAMS - 1) / S3_TEAMS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
@@ -1072,7 +1485,8 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
 {
     if (c1 <= c0) return HF_OK;
     if (!c->smem_attr[ATTR_WRITE]) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3L_SMEM));
         c->smem_attr[ATTR_WRITE] = true;
     }
     // units per run: a whole chunk per warp when that still gives every warp of the machine 16 runs or more (fewer
@@ -1082,8 +1496,15 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     const unsigned long long nruns = (c1 - c0) * ((DEC_THREADS / 32) / upw);
     unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
+    static int use_lut = -1;
+    if (use_lut < 0) { const char *e = getenv("HF_WRITE"); use_lut = (e && e[0] == '3') ? 0 : 1; }    // development switch (A/B timing)
+    if (use_lut) {
+        HF_PROF(c, "dec_write4_kernel");
+        dec_write3_kernel<true><<<(unsigned)grid, W3_THREADS, W3L_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
+    } else {
+        HF_PROF(c, "dec_write3_kernel");
+        dec_write3_kernel<false><<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
+    }
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

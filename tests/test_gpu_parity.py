@@ -142,6 +142,29 @@ def test_compress_fixtures_golden(codec, oracle, romeo, jpeg):
         assert sha(got) == gold[name]["compressed_sha256"]
 
 
+def test_compress_matches_reference_gpu_binary_hashes(codec):
+    """every file the UNMODIFIED reference GPU compressor wrote on a B200 (tests/golden/reference_hashes.json, made by
+    tests/golden/make_reference_hashes.py): the CUDA path must produce the same bytes — a pin that does not pass
+    through the oracle"""
+    gold = json.load(open(os.path.join(GOLDEN, "reference_hashes.json")))
+    small = small_cases()
+    inputs = {"pdf15m": lambda: dev(synth.pdf15m()), "zipf64m": lambda: synth.zipf1g(64 << 20, device="cuda"),
+              "zipf256m": lambda: synth.zipf1g(256 << 20, device="cuda"),
+              "romeo.txt": lambda: dev(np.fromfile(os.path.join(GOLDEN, "inputs", "romeo.txt"), dtype=np.uint8)),
+              "pexels.jpg": lambda: dev(np.fromfile(os.path.join(GOLDEN, "inputs", "pexels.jpg"), dtype=np.uint8))}
+    checked = 0
+    for name, g in gold.items():
+        make = inputs.get(name) or (lambda: dev(small[name[5:]]))
+        assert g["returncode"] == 0 and g["deterministic"] and g["reference_clean_domain"], name
+        d = make()
+        assert d.numel() == g["input_bytes"] and sha(d.cpu().numpy()) == g["input_sha256"], name
+        got = codec.compress(d).cpu().numpy()
+        assert got.size == g["compressed_bytes"], name
+        assert sha(got) == g["compressed_sha256"], name
+        checked += 1
+    assert checked >= 11
+
+
 def test_compress_pdf_standin_and_unaligned_output(codec, oracle):
     data = synth.pdf15m()
     want = oracle.compress(data)
@@ -524,7 +547,7 @@ def test_side_index_large_and_never_required(codec, oracle):
     prof = codec.profile_read()
     codec.profile(False)
     assert torch.equal(back, d)
-    assert "dec_sync3_kernel" not in prof and "dec_write3_kernel" in prof       # the synchronisation pass was skipped
+    assert not any(k.startswith("dec_sync") for k in prof) and any(k.startswith("dec_write") for k in prof)   # no synchronisation pass
     # a stale or damaged index is noticed and ignored
     bad = index.clone()
     pos = 64 + 2 * int(rng.integers(1000, bad.numel() // 2 - 1000))
