@@ -162,6 +162,7 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
         tab->t14[i] = entry;
         tab->t14s[i] = (entry & MICRO_FLAG) ? entry_s : entry;
         tab->d14[i] = dw;
+
     }
     if (i < (1u << k2)) {
         const uint32_t e = lookup_win32(tab, i << (32 - k2));
@@ -716,9 +717,15 @@ constexpr int S4_THREADS = 1024;
 constexpr int S4_WARPS = S4_THREADS / 32;
 constexpr uint32_t LANE_SUBS = DEC_THREADS / 32;                // 16
 constexpr uint32_t LANE_BITS = LANE_SUBS * SUB_BITS;            // 4096
-constexpr uint32_t ROW4_WORDS = SUB_BITS / 32 + 1;             // a subsequence + the word that follows it (odd: conflict-free)
-constexpr uint32_t REC4_WORDS = LANE_SUBS / 2 + 1;              // 16 u16 records + a pad word (odd)
-constexpr size_t S4_SMEM = (4u << MICRO_K) + (size_t)S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;
+// a warp's rows are stored column-major — word w of lane l at (w * 32 + l) — so a lane reads and writes its own bank
+// whatever word it is at (with one padded row per lane the lanes collide as soon as they drift apart inside a
+// subsequence: the walk is bound by shared-memory wavefronts and ALU issue about equally); the u16 records likewise
+constexpr uint32_t ROW4_WORDS = SUB_BITS / 32 + 1;             // a subsequence + the word that follows it
+constexpr uint32_t REC4_WORDS = LANE_SUBS / 2;                  // 16 u16 records
+constexpr uint32_t ROW4_STRIDE = 32 * 4;                        // bytes between consecutive words of a lane
+constexpr uint32_t REC4_STRIDE = 32 * 2;                        // bytes between consecutive records of a lane
+constexpr uint32_t S4_TAB_BYTES = 4u << MICRO_K;                // the d14 plane
+constexpr size_t S4_SMEM = S4_TAB_BYTES + (size_t)S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;
 static_assert(GROUP_CHUNKS == 1, "dec_sync4: a warp converges on one chunk");
 
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
@@ -775,24 +782,26 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
         if (!__any_sync(0xFFFFFFFFu, live)) break;
         if (live) {
             // my subsequence k: registers -> row (big-endian words); the next one goes in flight
-            sts32(row_a + 0, bswap32(na.x)); sts32(row_a + 4, bswap32(na.y)); sts32(row_a + 8, bswap32(na.z)); sts32(row_a + 12, bswap32(na.w));
-            sts32(row_a + 16, bswap32(nd.x)); sts32(row_a + 20, bswap32(nd.y)); sts32(row_a + 24, bswap32(nd.z)); sts32(row_a + 28, bswap32(nd.w));
-            sts32(row_a + 32, bswap32(nnext));
+            sts32(row_a + 0 * ROW4_STRIDE, bswap32(na.x)); sts32(row_a + 1 * ROW4_STRIDE, bswap32(na.y));
+            sts32(row_a + 2 * ROW4_STRIDE, bswap32(na.z)); sts32(row_a + 3 * ROW4_STRIDE, bswap32(na.w));
+            sts32(row_a + 4 * ROW4_STRIDE, bswap32(nd.x)); sts32(row_a + 5 * ROW4_STRIDE, bswap32(nd.y));
+            sts32(row_a + 6 * ROW4_STRIDE, bswap32(nd.z)); sts32(row_a + 7 * ROW4_STRIDE, bswap32(nd.w));
+            sts32(row_a + 8 * ROW4_STRIDE, bswap32(nnext));
             if (k + 1 < LANE_SUBS) load_sub_raw4(na, nd, nnext, S.frame, S.frame_bytes, span_byte0 + 32ull * (k + 1));
             const uint32_t sub0 = SUB_BITS * k;
             const uint32_t rel = pos - sub0;            // where this walk enters the subsequence (< 64 for codes <= 64 bits)
             if (have_rec && pos < lim) {                // entering where the earlier walk did: the walks have met
-                const uint32_t old = lds16(rec_a + 2u * k);
+                const uint32_t old = lds16(rec_a + REC4_STRIDE * k);
                 if (old >= 64u && rel == (old & 63u)) live = false;
             }
             if (live) {
                 const uint32_t lw = min(lim, sub0 + SUB_BITS);
                 uint32_t n = 0;
                 while (pos < lw) {
-                    const uint32_t wa = row_a + ((pos >> 3) & 28u);
-                    const uint32_t win = __funnelshift_l(lds32(wa + 4), lds32(wa), pos);
+                    const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
+                    const uint32_t win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
                     const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
-                    const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);
+                    const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
                     const bool micro = (e14 & 0xFu) != 0xCu;
                     uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
                     if (MULTI) {                        // all the code words the 14 bits hold, when they end inside the subsequence
@@ -810,7 +819,7 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
                     pos += len;
                     n += cnt;
                 }
-                sts16(rec_a + 2u * k, n ? ((rel & 63u) | (n << 6)) : 0u);
+                sts16(rec_a + REC4_STRIDE * k, n ? ((rel & 63u) | (n << 6)) : 0u);
             }
         }
     }
@@ -847,7 +856,7 @@ __device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, ui
         bool live = want && wstart < lim;
         if (want && !live) {                            // starts at or past my limit: no code word of mine
 #pragma unroll
-            for (uint32_t k = 0; k < LANE_SUBS; k += 2) sts32(rec_a + 2u * k, 0u);
+            for (uint32_t k = 0; k < LANE_SUBS; k++) sts16(rec_a + REC4_STRIDE * k, 0u);
             end = lim ? wstart - lim : 0u;
             rec_p = wstart; rec_end = end; have_rec = false;
         }
@@ -890,7 +899,7 @@ __device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, ui
     uint32_t r8[8], total = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        r8[i] = lds32(rec_a + 4u * i);
+        r8[i] = lds16(rec_a + REC4_STRIDE * (2 * i)) | (lds16(rec_a + REC4_STRIDE * (2 * i + 1)) << 16);
         total += ((r8[i] & 0xFFFFu) >> 6) + (r8[i] >> 22);
     }
     uint4 *dst = reinterpret_cast<uint4 *>(L.info + c * DEC_THREADS + lane * LANE_SUBS);
@@ -912,10 +921,11 @@ __device__ __forceinline__ void sync4_setup(uint32_t *smem, const DecodeTable *t
     const uint32_t tid = threadIdx.x;
     const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);           // lengths only
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S4_THREADS) dst[i] = __ldg(src + i);
+    for (uint32_t i = tid; i < S4_TAB_BYTES / 16; i += S4_THREADS) dst[i] = __ldg(src + i);
     d14_a = opaque_shared_addr(smem);
-    row_a = d14_a + (4u << MICRO_K) + tid * (ROW4_WORDS * 4u);
-    rec_a = d14_a + (4u << MICRO_K) + S4_THREADS * (ROW4_WORDS * 4u) + tid * (REC4_WORDS * 4u);
+    const uint32_t wid = tid >> 5, lane = tid & 31;
+    row_a = d14_a + S4_TAB_BYTES + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
+    rec_a = d14_a + S4_TAB_BYTES + S4_WARPS * (ROW4_WORDS * ROW4_STRIDE) + wid * (LANE_SUBS * REC4_STRIDE) + lane * 2u;
 }
 
 __global__ void __launch_bounds__(S4_THREADS, 1)
@@ -1497,7 +1507,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     static int use_lut = -1;
-    if (use_lut < 0) { const char *e = getenv("HF_WRITE"); use_lut = (e && e[0] == '3') ? 0 : 1; }    // development switch (A/B timing)
+    if (use_lut < 0) { const char *e = getenv("HF_WRITE"); use_lut = (e && e[0] == '4') ? 1 : 0; }    // development switch (A/B timing)
     if (use_lut) {
         HF_PROF(c, "dec_write4_kernel");
         dec_write3_kernel<true><<<(unsigned)grid, W3_THREADS, W3L_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
