@@ -16,7 +16,6 @@
 namespace hf {
 
 size_t codebook_alloc_bytes();          // codebook.cu
-int shapes_upload(Ctx *c);              // decode2.cu
 
 int set_err(Ctx *c, int code, const char *fmt, ...)
 {
@@ -117,7 +116,6 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     ok = ok && cudaMalloc(&c->d_hist, NSYM * 8 + 256) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_scan, SCAN_BLOCKS_MAX * 8) == cudaSuccess;
     ok = ok && ensure_ws(c, 1) == HF_OK;
-    ok = ok && shapes_upload(c) == HF_OK;
     if (!ok) { hf_ctx_destroy(reinterpret_cast<hf_ctx *>(c)); return HF_ERR_CUDA; }
     *out = reinterpret_cast<hf_ctx *>(c);
     return HF_OK;

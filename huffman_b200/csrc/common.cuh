@@ -99,20 +99,10 @@ struct DecodeTable {
     // (0x10C: not here, take the flat planes).  Else the micro tree as 16 two-bit fields, field j = (length at slot j)
     // - 15; a micro tree never has the low nibble 0xC: slot 0 at depth 1 covers slot 1 as well.
     alignas(16) uint32_t d14[1u << MICRO_K];
-    // t14s: t14 with a micro tree's leaf starts replaced by the number of its shape (SHAPE_* below), for the write
-    // kernel's table-driven micro decode: (base << 16) | 0x8000 | (shape << 4)
-    alignas(16) uint32_t t14s[1u << MICRO_K];
     alignas(16) uint16_t micro_sym[16u << MICRO_K];     // build scratch: symbol at every slot of every prefix
     alignas(16) uint8_t lenflat[1u << FLAT_MAX];
     alignas(16) uint32_t flat2[1u << FLAT_MAX];
 };
-
-// Shapes of micro trees: a complete binary tree of depth <= 4 whose root is split has one of SHAPE_COUNT shapes
-// (a(4) - 1, a(n) = a(n-1)^2 + 1).  shape_id maps the leaf-start bits of slots 1..15 to the shape's number (0xFFFF: not
-// a tree); shape_lut[shape * 16 + slot] = (code length - 15) | (2 * rank of the slot's leaf) << 2.  Filled once per
-// device by shapes_upload (decode2.cu).
-constexpr uint32_t SHAPE_COUNT = 676;
-constexpr uint32_t SHAPE_LUT_BYTES = SHAPE_COUNT * 16;
 
 // ---- context ----------------------------------------------------------------------
 struct Ctx {

@@ -1,4 +1,4 @@
-// decode2.cu — the hot kernels of the decoder: dec_sync3_kernel (code word boundaries and symbol counts per
+// decode2.cu — the hot kernels of the decoder: dec_sync4_kernel (code word boundaries and symbol counts per
 // 256-bit subsequence), dec_fix2_kernel (inter-group repair) and dec_write3_kernel (symbols out), plus the
 // shared-memory table planes they read.  decode.cu holds the header parser, the general tables, the scan and
 // the orchestration; the kernels meet in the work area of decode_common.cuh (DecLayout: info / chunkCnt / chunkE).
@@ -20,16 +20,15 @@
 //     need 1 MiB; here every code of up to 18 bits is resolved without leaving the SM.  Deeper or incomplete
 //     prefixes take ONE gather from a flat second-level plane (<= 22 bits, L2 resident); anything beyond goes
 //     through decode.cu's tables;
-//   * re-synchronisation is detected at checkpoints every 128 bits (the first code word boundary at or after
-//     the checkpoint, with the symbol count of every segment), which costs two instructions per checkpoint
-//     instead of a 256-bit boundary mask maintained per symbol;
+//   * the synchronisation kernel gives every warp a whole chunk and every lane a 512-byte span of it (round 1 gave a
+//     thread 128 bytes and converged in teams of four warps behind named barriers: 40 % of its walk iterations were
+//     repeated walks, 17 % of its stalls barrier waits); the per-subsequence records double as the checkpoints at which
+//     a repeated walk recognises the earlier one;
 //   * what the per-source-line and per-SASS-instruction views of ncu found later is listed in profiles/README.md
 //     (shared-memory base addresses rebuilt inside loops, loop state in local memory around a call, loads that
 //     were waited for where they were issued, single-lane tails).
 //
-// Algorithmic bytes: dec_sync3 reads C; dec_write3 reads C and writes N.
-#include <stdlib.h>
-
+// Algorithmic bytes: dec_sync4 reads C; dec_write3 reads C and writes N.
 #include "common.cuh"
 #include "decode_common.cuh"
 
@@ -42,49 +41,6 @@ constexpr uint32_t MICRO_MAX = MICRO_K + MICRO_D;               // longest code 
 constexpr uint32_t MICRO_FLAG = 0x8000u;
 __host__ __device__ __forceinline__ uint32_t micro_starts(uint32_t e) { return ((e & 0x7FFFu) << 1) | 1u; }
 __device__ __forceinline__ uint32_t micro_leaves(uint32_t e) { return __popc(e & 0x7FFFu) + 1u; }
-// ---- micro-tree shapes (common.cuh) ----------------------------------------------------------------
-__device__ uint16_t g_shape_id[1u << 15];
-__device__ __align__(16) uint8_t g_shape_lut[SHAPE_LUT_BYTES];
-
-int shapes_upload(Ctx *c)
-{
-    static uint16_t h_id[1u << 15];
-    static uint8_t h_lut[SHAPE_LUT_BYTES];
-    static bool built = false;
-    if (!built) {
-        uint32_t n = 0;
-        for (uint32_t m15 = 0; m15 < (1u << 15); m15++) {
-            const uint32_t mask = (m15 << 1) | 1u;      // bit j: a leaf starts at slot j
-            bool valid = true;
-            for (uint32_t s0 = 0; s0 < 16 && valid;) {
-                uint32_t e = s0 + 1;
-                while (e < 16 && !((mask >> e) & 1u)) e++;
-                const uint32_t r = e - s0;               // slots of this leaf: 1, 2, 4 or 8, aligned
-                if (r == 16 || (r & (r - 1)) || (s0 & (r - 1))) valid = false;
-                s0 = e;
-            }
-            h_id[m15] = 0xFFFFu;
-            if (!valid || n >= SHAPE_COUNT) continue;
-            for (uint32_t b = 0; b < 16; b++) {
-                uint32_t s0 = b;
-                while (!((mask >> s0) & 1u)) s0--;
-                uint32_t e = s0 + 1;
-                while (e < 16 && !((mask >> e) & 1u)) e++;
-                uint32_t lg = 0;
-                while ((1u << lg) < e - s0) lg++;
-                const uint32_t rank = (uint32_t)__builtin_popcount(mask & ((2u << b) - 1u)) - 1u;
-                h_lut[n * 16 + b] = (uint8_t)((3u - lg) | ((2u * rank) << 2));
-            }
-            h_id[m15] = (uint16_t)n++;
-        }
-        if (n != SHAPE_COUNT) return set_err(c, HF_ERR_INTERNAL, "micro-tree shapes: %u, expected %u", n, SHAPE_COUNT);
-        built = true;
-    }
-    HF_CUDA(c, cudaMemcpyToSymbol(g_shape_id, h_id, sizeof(h_id)));
-    HF_CUDA(c, cudaMemcpyToSymbol(g_shape_lut, h_lut, sizeof(h_lut)));
-    return HF_OK;
-}
-
 #ifndef W3_WARPS
 #define W3_WARPS 24                                             // warps of the write kernel's CTA
 #endif
@@ -95,10 +51,6 @@ constexpr int W3_THREADS = W3_WARPS * 32;
 // output staging window of one warp (symbols, multiple of 8): what is left of the SM's 227 KiB beside the planes
 constexpr uint32_t W3_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - 64u) / W3_WARPS) / 2 - 8) & ~7u;
 constexpr size_t W3_SMEM = (4u << MICRO_K) + NSYM * 2 + (size_t)W3_WARPS * (W3_WIN + 8) * 2;
-// the same with the shape table (SHAPE_LUT_PAD bytes) between the planes and the windows
-constexpr uint32_t SHAPE_LUT_PAD = (SHAPE_LUT_BYTES + 63u) & ~63u;
-constexpr uint32_t W3L_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - SHAPE_LUT_PAD - 64u) / W3_WARPS) / 2 - 8) & ~7u;
-constexpr size_t W3L_SMEM = (4u << MICRO_K) + NSYM * 2 + SHAPE_LUT_PAD + (size_t)W3_WARPS * (W3L_WIN + 8) * 2;
 
 // ---- planes ------------------------------------------------------------------------------------
 // (sym << 8) | len of the code word that is a prefix of the left-aligned window, from t1 / t2; 0 when
@@ -125,7 +77,7 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
         // entry of the 14-bit prefix i: a short code, or the shape of the micro tree below it
         const uint32_t w0 = i << (32 - MICRO_K);
         const uint32_t e0 = lookup_win32(tab, w0);
-        uint32_t entry = 0, entry_s = 0, dw = 0x10Cu;     // not here: no bits, counted as one code word by the flat path
+        uint32_t entry = 0, dw = 0x10Cu;                  // not here: no bits, counted as one code word by the flat path
         if (e0 && (e0 & 0x7Fu) <= MICRO_K) {
             entry = ((e0 >> 8) << 16) | ((e0 & 0x7Fu) << 1);
             // the lengths-only twin also says how many code words these 14 bits hold completely, and their bits
@@ -155,12 +107,9 @@ __global__ void dt_planes_kernel(DecodeTable *__restrict__ tab)
                 const uint32_t d = (depths >> (2 * j)) & 3u, first = j & ~((8u >> d) - 1u);
                 if (((depths >> (2 * first)) & 3u) != d) ok = false;
             }
-            uint32_t sid = ok ? g_shape_id[mask >> 1] : 0xFFFFu;
-            if (sid == 0xFFFFu) ok = false;
-            if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; entry_s = (sid << 4) | MICRO_FLAG; }   // the base comes from dt_micro_kernel
+            if (ok) { entry = (mask >> 1) | MICRO_FLAG; dw = depths; }      // the base comes from dt_micro_kernel
         }
         tab->t14[i] = entry;
-        tab->t14s[i] = (entry & MICRO_FLAG) ? entry_s : entry;
         tab->d14[i] = dw;
 
     }
@@ -181,7 +130,6 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
     constexpr uint32_t PER = (1u << MICRO_K) / 1024;    // 16 prefixes per thread
     uint4 v[PER / 4];
     uint4 *ent = reinterpret_cast<uint4 *>(tab->t14 + tid * PER);
-    uint32_t *ent_s = tab->t14s + tid * PER;
     uint32_t sum = 0;
 #pragma unroll
     for (uint32_t j = 0; j < PER / 4; j++) {
@@ -211,9 +159,7 @@ dt_micro_kernel(DecodeTable *__restrict__ tab)
         for (int k = 0; k < 4; k++) {
             if (!(e4[k] & MICRO_FLAG)) continue;
             const uint32_t shape = e4[k] & 0xFFFFu, n = micro_leaves(shape);
-            const bool fits = base + n <= NSYM;                         // cannot overflow for a prefix code
-            e4[k] = fits ? ((base << 16) | shape) : 0u;
-            ent_s[4 * j + k] = fits ? ((base << 16) | (ent_s[4 * j + k] & 0xFFFFu)) : 0u;
+            e4[k] = base + n > NSYM ? 0u : ((base << 16) | shape);      // cannot overflow for a prefix code
             base += n;
         }
         ent[j] = make_uint4(e4[0], e4[1], e4[2], e4[3]);
@@ -315,27 +261,7 @@ __device__ __forceinline__ void finish_sub(uint32_t (&r)[9], const uint32_t (&ra
     r[8] = lane == 31 ? bswap32(raw[8]) : nx;
 }
 
-// ---- synchronisation kernel ---------------------------------------------------------------------
-// A thread walks a SPAN of 4 subsequences (1024 bits).  Longer spans mean fewer repeated walks: a walk
-// from a wrong start re-joins the true one after tens of bits on skewed codes but only after ~2,000 bits
-// on the nearly fixed-length codes of flat data, and every subsequence a wrong walk crosses costs the
-// fix-point one more round.  A CTA of 1024 threads holds 8 TEAMS of 4 warps; a team stages its own GROUP (one
-// chunk, 16 KiB) in shared memory, one padded row of 33 words per thread (bank = (thread + word) mod 32; the pad
-// word repeats the next row's first word so a 32-bit window never leaves the row), and converges on it behind its
-// own named barrier.  Small teams wait less on their slowest warp (teams of 8 warps: +7 % kernel time, of 16: +15 %);
-// the price is one more group boundary per chunk for the repair pass, which is cheap.
-constexpr int S3_THREADS = 1024;
-constexpr int TEAM_THREADS = DEC_TEAM_THREADS;
-constexpr int S3_TEAMS = S3_THREADS / TEAM_THREADS;
-constexpr uint32_t SPAN_SUBS = DEC_SPAN_SUBS;
-constexpr uint32_t SPAN_BITS = SPAN_SUBS * SUB_BITS;            // 1024
-constexpr uint32_t SPAN_WORDS = SPAN_BITS / 32;                 // 32
-constexpr uint32_t ROW_WORDS = SPAN_WORDS + 1;
-constexpr unsigned long long GROUP_BITS = (unsigned long long)TEAM_THREADS * SPAN_BITS;
-constexpr uint32_t SEG_BITS = 128;                              // checkpoint spacing
-constexpr uint32_t NSEG = SPAN_BITS / SEG_BITS;                 // 8
-constexpr size_t S3_SMEM = (4u << MICRO_K) + (size_t)S3_THREADS * ROW_WORDS * 4;
-
+// ---- shared-memory access by 32-bit address -------------------------------------------------------
 // the 32-bit shared address of p, passed through a shuffle so that the compiler keeps it in a register instead of
 // re-deriving it (S2UR SR_CgaCtaId + three uniform ops) at every use; call with the whole warp
 __device__ __forceinline__ uint32_t opaque_shared_addr(const void *p)
@@ -349,13 +275,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t shared_addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
     return v;
 }
-
-__device__ __forceinline__ uint32_t lds8s(uint32_t shared_addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t lds16(uint32_t a)
 {
     uint32_t v;
@@ -363,350 +282,13 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a)
     return v;
 }
 
-// Record of a walk: chkpos byte k = (first code word boundary at or after bit 128k) - 128k; chkcnt byte k = code
-// words starting in [128k, 128k + 128).  CHK_NONE (bytes 0xFF, no checkpoint offset is that large) = no walk yet.
-struct Chk { uint32_t pos[2], cnt[2]; };
-constexpr uint32_t CHK_NONE = 0xFFFFFFFFu;
-
-// Walks the code words of a span from bit `start` to `lim`.  RESYNC: `rec` describes an earlier walk; stop at
-// the first checkpoint both walks share and keep the earlier record from there on (`end` stays the earlier one's).
-template <bool RESYNC, bool MULTI>
-__device__ __forceinline__ void walk_span(const uint32_t *row, uint32_t t14_a, const DecodeTable *tab,
-                                          const uint8_t *frame, unsigned long long frame_bytes,
-                                          unsigned long long span_bit0, uint32_t k2shift, uint32_t start, uint32_t lim,
-                                          Chk &rec, uint32_t &end, uint32_t &bad)
-{
-    uint32_t pos = start, n = 0, wl = lim;
-    uint32_t npos[2] = {0, 0}, ncnt[2] = {0, 0};
-    // t14_a: the table's 32-bit shared address as a plain register value (opaque_shared_addr); left to itself the
-    // compiler rebuilds the shared window base inside every walk loop, four uniform instructions per code word
-    const uint32_t row_a = (uint32_t)__cvta_generic_to_shared(row);
-    int kept = NSEG;                                    // checkpoints >= kept keep the earlier record
-#pragma unroll
-    for (int k = 0; k < (int)NSEG; k++) {
-        if (k > 0) { ncnt[(k - 1) >> 2] |= n << (8 * ((k - 1) & 3)); n = 0; }
-        const uint32_t rel = (pos - SEG_BITS * k) & 0xFFu;
-        if (RESYNC && k > 0) {          // still walking, and on the earlier walk's boundary: the walks have met
-            if (pos < wl && rel == ((rec.pos[k >> 2] >> (8 * (k & 3))) & 0xFFu)) { wl = 0; kept = k; }
-        }
-        npos[k >> 2] |= rel << (8 * (k & 3));
-        const uint32_t lw = min(wl, SEG_BITS * (k + 1));
-        while (pos < lw) {
-            const uint32_t wa = row_a + ((pos >> 5) << 2);
-            const uint32_t win = __funnelshift_l(lds32(wa + 4), lds32(wa), pos);
-            const uint32_t e14 = lds32(t14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));    // the d14 plane
-            const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
-            const bool micro = (e14 & 0xFu) != 0xCu;
-            uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
-            if (MULTI) {                            // all the code words the 14 bits hold, when they end inside the segment
-                const uint32_t tot = (e14 >> 4) & 0xFu;
-                if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
-            }
-            if (len == 0) {
-                len = __ldg(tab->lenflat + (win >> k2shift));
-                if (len == 0) {
-                    const uint32_t e = slow_decode(tab, frame, frame_bytes, span_bit0 + pos);
-                    bad |= e >> 31;
-                    len = e & 0x7Fu;
-                }
-            }
-            pos += len;
-            n += cnt;
-        }
-    }
-    ncnt[1] |= n << 24;
-    if (RESYNC && kept < (int)NSEG) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            // bytes of half h that belong to checkpoints >= kept
-            const int first = kept - 4 * h;             // first kept byte of this half (may be <= 0 or >= 4)
-            const uint32_t keep = first <= 0 ? 0xFFFFFFFFu : (first >= 4 ? 0u : 0xFFFFFFFFu << (8 * first));
-            rec.pos[h] = (npos[h] & ~keep) | (rec.pos[h] & keep);
-            rec.cnt[h] = (ncnt[h] & ~keep) | (rec.cnt[h] & keep);
-        }
-    } else {
-        rec.pos[0] = npos[0]; rec.pos[1] = npos[1];
-        rec.cnt[0] = ncnt[0]; rec.cnt[1] = ncnt[1];
-        end = pos - lim;
-    }
-}
-
-__device__ __forceinline__ uint32_t span_limit(unsigned long long X, unsigned long long range_end_bit)
-{   // bits of the span at frame bit X that lie before the end of the range (0 .. SPAN_BITS)
-    if (X >= range_end_bit) return 0u;
-    const unsigned long long room = range_end_bit - X;
-    return room >= SPAN_BITS ? SPAN_BITS : (uint32_t)room;
-}
-
-__device__ __forceinline__ void team_sync(uint32_t team)
-{
-    asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TEAM_THREADS) : "memory");
-}
-__device__ __forceinline__ bool team_or(uint32_t team, bool pred)
-{
-    uint32_t r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"((uint32_t)pred), "r"(team + 1), "r"(TEAM_THREADS) : "memory");
-    return r != 0;
-}
-
-// what the threads of a synchronisation CTA share
-struct SyncCtx {
-    const uint8_t *frame;
-    unsigned long long frame_bytes, F0, range_end_bit, nch;
-    const DecodeTable *tab;
-    DecWork *work;
-    uint32_t t14_a;                     // shared address of the d14 plane (opaque_shared_addr)
-    uint32_t *s_bits, *s_wend, *s_red;
-    uint32_t g, k2shift;                // gcd of the code lengths (1 when speculating), 32 - k2
-};
-
-// One team converges on one group (GROUP_CHUNKS chunks): per-subsequence records, chunk totals and overflows.
-// exact: the group's first code word starts `start` bits into it (the stream head, or the true overflow of the group
-// before when a group is redone); otherwise the first span starts from a guess like every other one.
-// dense: code words my warp counted in the group before (0 at first).  Short code words come several to a 14-bit
-// look-up; when the warp's last 32 Kbit held more than DENSE_MIN of them (under ~10 bits each) the walks take all the
-// code words an entry holds in one step (walk_span<.., true>), which costs every step a few instructions more.
-constexpr uint32_t DENSE_MIN = 32u * SPAN_BITS / 10u;
-__device__ __forceinline__ void sync_group(const SyncCtx &S, unsigned long long grp, bool exact, uint32_t start, uint32_t &bad,
-                                           uint32_t &dense)
-{
-    const bool multi = dense > DENSE_MIN;
-    const uint8_t *frame = S.frame;
-    const unsigned long long frame_bytes = S.frame_bytes, F0 = S.F0, range_end_bit = S.range_end_bit, nch = S.nch;
-    const DecodeTable *tab = S.tab;
-    DecWork *work = S.work;
-    const uint32_t t14_a = S.t14_a;
-    uint32_t *s_bits = S.s_bits, *s_wend = S.s_wend, *s_red = S.s_red;
-    const uint32_t g = S.g, k2shift = S.k2shift;
-    DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t team = tid / TEAM_THREADS, tt = tid % TEAM_THREADS;      // my team, my index in it
-    const uint32_t *row = s_bits + tid * ROW_WORDS;
-    uint32_t *team_rows = s_bits + team * TEAM_THREADS * ROW_WORDS;
-
-    team_sync(team);                                // my team's rows, s_wend, s_red are free again
-    // ---- stage the group: 8 coalesced 128-bit loads per thread ----
-    const unsigned long long gbyte0 = grp * (GROUP_BITS / 8);
-#pragma unroll
-    for (uint32_t k = 0; k < SPAN_WORDS / 4; k++) {
-        const uint32_t v = tt + k * TEAM_THREADS;   // 16-byte vector of the group
-        const unsigned long long b = gbyte0 + 16ull * v;
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (b < frame_bytes) x = ld_stream_v4(frame + b);          // the frame is 16-byte aligned
-        uint32_t *dst = team_rows + (v >> 3) * ROW_WORDS + 4 * (v & 7);
-        dst[0] = bswap32(x.x); dst[1] = bswap32(x.y); dst[2] = bswap32(x.z); dst[3] = bswap32(x.w);
-    }
-    {   // the pad word of my row: the first word of the next span
-        const unsigned long long b = gbyte0 + (unsigned long long)(tt + 1) * (SPAN_BITS / 8);
-        uint32_t x = 0;
-        if (b < frame_bytes) x = bswap32(__ldg(reinterpret_cast<const uint32_t *>(frame + b)));
-        s_bits[tid * ROW_WORDS + SPAN_WORDS] = x;
-    }
-    team_sync(team);
-
-    const unsigned long long X = grp * GROUP_BITS + (unsigned long long)tt * SPAN_BITS;
-    const uint32_t lim = span_limit(X, range_end_bit);     // code words starting at or after the range end are not ours
-    const bool fixed = exact && tt == 0;                    // exact: the group's first code word starts at `start`
-    uint32_t p = fixed ? start : (X >= F0 ? spec_start(X, F0, g) : 0u);
-    uint32_t end = 0;
-    Chk rec{{CHK_NONE, CHK_NONE}, {0, 0}};
-    // `rec` describes the walk from rec_p, which ended at rec_end.  memo: up to four (start + 1, end) pairs of
-    // walks this thread has done on this span.  Data that does not re-synchronise (a long run of one code word
-    // is periodic: a walk that enters it out of phase leaves it out of phase) makes the fix-point hand a lane
-    // the same few starts again and again; a remembered start costs no walk, and the record of the final start
-    // is rebuilt once at the end.
-    uint32_t rec_p = p, rec_end = 0, mslot = 0, nwalk = 0;
-    unsigned long long memo = 0;
-    auto memo_add = [&](uint32_t st, uint32_t en) {
-        memo = (memo & ~(0xFFFFull << (16 * mslot))) | ((unsigned long long)(((st + 1) << 8) | en) << (16 * mslot));
-        mslot = (mslot + 1) & 3;
-        nwalk++;
-    };
-    if (lim) {
-        if (p < lim) {
-            if (multi) walk_span<false, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
-            else walk_span<false, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
-            memo_add(p, end);
-        }
-        else end = p - lim;
-        rec_end = end;
-    }
-    // Fix-point: my true start is my predecessor's overflow.  Inside a warp the overflows travel by
-    // shuffle and the warps iterate on their own; the warps then exchange their last overflow through
-    // shared memory, which usually moves only lane 0 of each warp.
-    const bool movable = !fixed && lim != 0;
-    uint32_t q0 = p;                                // lane 0's start: the guess, then the previous warp's overflow
-    for (uint32_t round = 0; round < TEAM_THREADS / 32 + 2; round++) {
-        for (;;) {
-            uint32_t q = __shfl_up_sync(0xFFFFFFFFu, end, 1);
-            if (lane == 0) q = q0;
-            const bool need = movable && q != p;
-            if (!__any_sync(0xFFFFFFFFu, need)) break;
-            if (need) {
-                uint32_t hit = 0;                   // ((q + 1) << 8) | end of a walk from q done before
-                if (nwalk >= 2) {                   // the first correction of a guess cannot be a repeat
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t en = (uint32_t)(memo >> (16 * j)) & 0xFFFFu;
-                        if ((en >> 8) == q + 1) hit = en;
-                    }
-                }
-                if (hit) {
-                    end = hit & 0xFFu;              // rec stays with the walk it describes
-                } else if (q < lim) {
-                    end = rec_end;                  // a merge keeps the recorded walk's end
-                    if (multi) walk_span<true, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
-                    else walk_span<true, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, q, lim, rec, end, bad);
-                    rec_p = q; rec_end = end;
-                    memo_add(q, end);
-                } else {
-                    rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = q - lim;
-                    rec_p = q; rec_end = end;
-                }
-                p = q;
-            }
-        }
-        if (lane == 31) s_wend[wid] = end;
-        team_sync(team);
-        q0 = (tt >> 5) ? s_wend[wid - 1] : p;
-        if (!team_or(team, lane == 0 && movable && q0 != p)) break;
-    }
-    if (lim && rec_p != p) {                        // the final start was a remembered one: rebuild its record
-        if (p < lim) {
-            end = rec_end;
-            if (multi) walk_span<true, true>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
-            else walk_span<true, false>(row, t14_a, tab, frame, frame_bytes, X, k2shift, p, lim, rec, end, bad);
-        } else {
-            rec.pos[0] = rec.pos[1] = CHK_NONE; rec.cnt[0] = rec.cnt[1] = 0; end = p - lim;
-        }
-    }
-
-    // ---- per-subsequence records: start offset (6 bits) | code words (10 bits), 4 per thread ----
-    uint32_t cnt4[SPAN_SUBS];
-    uint32_t total = 0;
-    unsigned long long packed = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < SPAN_SUBS; j++) {
-        const uint32_t pj = (rec.pos[j >> 1] >> (16 * (j & 1))) & 0xFFu;            // checkpoint 2j
-        const uint32_t cj = (rec.cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;          // segments 2j, 2j + 1
-        cnt4[j] = (cj & 0xFFu) + (cj >> 8);
-        total += cnt4[j];
-        packed |= (unsigned long long)((pj & 63u) | (cnt4[j] << 6)) << (16 * j);
-    }
-    const unsigned long long sub_index = grp * (GROUP_BITS / SUB_BITS) + (unsigned long long)tt * SPAN_SUBS;
-    if (sub_index < nch * DEC_THREADS)              // info holds whole chunks: 4 records never straddle its end
-        *reinterpret_cast<unsigned long long *>(L.info + sub_index) = packed;
-    // chunk totals: a chunk is 128 consecutive threads (4 warps)
-    uint32_t v = total;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) s_red[wid] = v;
-    dense = v;
-    team_sync(team);
-    constexpr uint32_t TPC = DEC_THREADS / SPAN_SUBS;       // threads per chunk
-    const unsigned long long c = grp * GROUP_CHUNKS + tt / TPC;
-    if (c < nch) {
-        if (tt % TPC == 0) {
-            uint32_t tot = 0;
-#pragma unroll
-            for (uint32_t i = 0; i < TPC / 32; i++) tot += s_red[wid + i];
-            L.chunkCnt[c] = tot;
-            L.chunkE2[c] = 0xFFFFFFFFu;
-        }
-        if (tt % TPC == TPC - 1) L.chunkE[c] = end;
-    }
-    // the thread whose span holds the end of the range reports the overflow past it
-    if (lim && span_limit(X + SPAN_BITS, range_end_bit) == 0) work->result[1] = end;
-}
-
-__global__ void __launch_bounds__(S3_THREADS, 1)
-dec_sync3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
-                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                 unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative)
-{
-    extern __shared__ __align__(16) uint32_t s3_smem[];
-    uint32_t *s_t14 = s3_smem;                          // 2^MICRO_K
-    uint32_t *s_bits = s3_smem + (1u << MICRO_K);       // S3_THREADS rows of ROW_WORDS
-    __shared__ uint32_t s_wend[S3_THREADS / 32];
-    __shared__ uint32_t s_red[S3_THREADS / 32];
-    if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
-    const uint32_t tid = threadIdx.x, team = tid / TEAM_THREADS;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);       // lengths only
-        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
-        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
-    }
-    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, opaque_shared_addr(s_t14), s_bits, s_wend, s_red,
-                    speculative ? 1u : tab->len_gcd, 32u - tab->k2};
-    uint32_t bad = 0;
-    __syncthreads();                                    // planes loaded
-
-    uint32_t dense = 0;
-    for (unsigned long long grp = g_first + (unsigned long long)blockIdx.x * S3_TEAMS + team; grp < g_last;
-         grp += (unsigned long long)gridDim.x * S3_TEAMS)
-        sync_group(S, grp, grp == 0 && !speculative, (uint32_t)F0, bad, dense);
-    if (bad) atomicExch(&work->flags[1], 1ull);
-}
-
-// Groups the cheap repair (dec_fix2_kernel) gave up on: the chain of the group before never meets the chain the
-// group recorded from its guessed start (data that does not re-synchronise, e.g. a long run of one code word).
-// A team takes the head of every run of such groups and redoes the groups one after the other from their TRUE
-// starts, walking on into the following groups for as long as the overflow it hands over is not the start they
-// recorded.  Runs are independent of each other; a chain that reaches another run's groups is caught by
-// dec_verify_kernel and settled by the serial kernel.
+// Groups the cheap repair (dec_fix2_kernel) gave up on are marked in chunkE2 of their first chunk
 constexpr uint32_t CHUNK_DIRTY = 0xFFFFFFFEu;           // in chunkE2 of a group's first chunk
-
-__global__ void __launch_bounds__(S3_THREADS, 1)
-dec_regroup_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
-                   unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                   unsigned long long nch, unsigned long long g_first, unsigned long long g_last, uint32_t speculative)
-{
-    if (work->flags[3] == 0) return;                    // no group was given up on
-    extern __shared__ __align__(16) uint32_t s3_smem[];
-    uint32_t *s_t14 = s3_smem;
-    uint32_t *s_bits = s3_smem + (1u << MICRO_K);
-    __shared__ uint32_t s_wend[S3_THREADS / 32];
-    __shared__ uint32_t s_red[S3_THREADS / 32];
-    if (tab->single_sym) return;
-    DecLayout L(work, nch);
-    const uint32_t tid = threadIdx.x, team = tid / TEAM_THREADS;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
-        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += S3_THREADS) dst[i] = __ldg(src + i);
-    }
-    const SyncCtx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, opaque_shared_addr(s_t14), s_bits, s_wend, s_red,
-                    speculative ? 1u : tab->len_gcd, 32u - tab->k2};
-    uint32_t bad = 0;
-    __syncthreads();
-
-    const unsigned long long g_lo = g_first ? g_first : 1;      // the first group of a stream has an exact start
-    uint32_t dense = 0;
-    for (unsigned long long g = g_lo + (unsigned long long)blockIdx.x * S3_TEAMS + team; g < g_last;
-         g += (unsigned long long)gridDim.x * S3_TEAMS) {
-        // the head of a run: given up on, and the group before was not
-        if (L.chunkE2[g * GROUP_CHUNKS] != CHUNK_DIRTY) continue;
-        if (g > g_lo && L.chunkE2[(g - 1) * GROUP_CHUNKS] == CHUNK_DIRTY) continue;
-        for (unsigned long long cur = g;;) {
-            const uint32_t s = L.chunkE[cur * GROUP_CHUNKS - 1];    // final: the group before is settled
-            sync_group(S, cur, true, s, bad, dense);                // also resets chunkE2 of its chunks
-            team_sync(team);                                        // the group's records are in global memory
-            const unsigned long long next = cur + 1;
-            if (next >= g_last) break;
-            const bool dirty = L.chunkE2[next * GROUP_CHUNKS] == CHUNK_DIRTY;
-            const bool meets = L.chunkE[next * GROUP_CHUNKS - 1] == (uint32_t)(L.info[next * GROUP_CHUNKS * DEC_THREADS] & 63u);
-            if (!dirty && meets) break;
-            cur = next;
-        }
-    }
-    if (bad) atomicExch(&work->flags[1], 1ull);
-}
 
 // -------------------------------------------------------------------------------------------------
 // dec_sync4_kernel: every WARP converges on one chunk by itself (no teams, no CTA or named barriers after the
 // table load).  A lane owns LANE_SUBS = 16 consecutive subsequences (512 bytes of payload): four times the span
-// of dec_sync3's threads, so a guessed start costs a quarter as many repeated walks per payload bit (a wrong
+// of round 1's team kernel, so a guessed start costs a quarter as many repeated walks per payload bit (a wrong
 // walk re-joins the true chain after tens of bits on skewed codes, after ~2,000 bits on the nearly fixed-length
 // codes of flat data).  The lane streams its span through a private shared-memory row, two subsequences (64
 // bytes, two whole sectors) at a time; the next pair is in flight in registers while this one is walked.  The
@@ -829,7 +411,10 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
 // One warp converges on chunk c.  exact: the chunk's first code word starts `start` bits into it (the stream head,
 // or the true overflow of the chunk before when a chunk is redone); otherwise lane 0 starts from a guess like every
 // other lane and dec_fix2_kernel repairs the chunk's first subsequences afterwards.  dense: code words this warp
-// counted in its last chunk (see DENSE_MIN).  mark: reset the chunk's repair mark (the regroup kernel must not).
+// counted in its last chunk (see DENSE4_MIN).  mark: reset the chunk's repair mark (the regroup kernel must not).
+// Short code words come several to a 14-bit look-up; when the warp's last chunk held more than DENSE4_MIN of them (under
+// ~10 bits each) the walks take all the code words an entry holds in one step (MULTI), which costs every step a few
+// instructions more.
 constexpr uint32_t DENSE4_MIN = CHUNK_BITS / 10u;
 template <bool MULTI>
 __device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, uint32_t rec_a, unsigned long long c,
@@ -1029,10 +614,6 @@ __global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *
 // Every WARP works on its own: a unit of 32 consecutive subsequences (1 KiB of payload), whose output offset
 // it derives itself from the chunk's records (no CTA-wide scan, no CTA barrier after the planes are loaded).
 // The symbols of a unit are compacted in the warp's staging window and leave with aligned 128-bit stores.
-// LUT: the micro trees are decoded with the shape table (t14s + g_shape_lut: two dependent shared-memory loads and
-// nine ALU instructions for a 15..18-bit code) instead of bit arithmetic on the leaf starts (t14: eighteen, five of
-// them bit-find / bit-reverse / population counts).
-template <bool LUT>
 __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
@@ -1040,30 +621,22 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                   uint16_t *__restrict__ out, uint32_t check, uint32_t upw)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
-    constexpr uint32_t WIN = LUT ? W3L_WIN : W3_WIN;
+    constexpr uint32_t WIN = W3_WIN;
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
     uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
-    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_leaves + NSYM);              // SHAPE_LUT_PAD (LUT only)
     if (tab->single_sym) return;
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint16_t *sout = reinterpret_cast<uint16_t *>(s_lut + (LUT ? SHAPE_LUT_PAD : 0u)) + wid * (WIN + 8);   // this warp's window
+    uint16_t *sout = s_leaves + NSYM + wid * (WIN + 8);                         // this warp's window
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(LUT ? tab->t14s : tab->t14);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
         for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
         src = reinterpret_cast<const uint4 *>(tab->leaves);
         dst = reinterpret_cast<uint4 *>(s_leaves);
         for (uint32_t i = tid; i < NSYM * 2 / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
-        if (LUT) {
-            src = reinterpret_cast<const uint4 *>(g_shape_lut);
-            dst = reinterpret_cast<uint4 *>(s_lut);
-            for (uint32_t i = tid; i < SHAPE_LUT_BYTES / 16; i += W3_THREADS) dst[i] = src[i];
-        }
     }
     __syncthreads();
-    const uint32_t lut_a = opaque_shared_addr(s_lut);
-    const uint32_t leaves_a1 = lut_a - NSYM * 2 - 1u;               // (entry >> 15) = 2 * base + 1 for a micro entry
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t bad = 0;
     constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
@@ -1138,15 +711,9 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
                         uint32_t len, sym;
                         if (e14 & MICRO_FLAG) {
-                            if (LUT) {
-                                const uint32_t x = lds8s(lut_a + (e14 & 0x3FF0u) + ((win >> (32 - MICRO_MAX)) & 15u));
-                                len = (MICRO_K + 1) + (x & 3u);
-                                sym = lds16(leaves_a1 + (e14 >> 15) + (x >> 2));
-                            } else {
-                                uint32_t leaf;
-                                micro_decode(e14, win, len, leaf);
-                                sym = s_leaves[leaf];
-                            }
+                            uint32_t leaf;
+                            micro_decode(e14, win, len, leaf);
+                            sym = s_leaves[leaf];
                         } else {
                             len = (e14 >> 1) & 0x7Fu;
                             sym = e14 >> 16;
@@ -1407,14 +974,6 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
     work->flags[0] = 0;                                 // settled (the next slice starts clean)
 }
 
-// development switch (A/B timing): HF_SYNC=3 selects the team-based synchronisation kernels
-static bool use_sync3()
-{
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("HF_SYNC"); v = (e && e[0] == '3') ? 1 : 0; }
-    return v == 1;
-}
-
 // chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
 int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
@@ -1427,19 +986,11 @@ int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, un
     HF_CUDA(c, cudaMemsetAsync(&work->flags[3], 0, 8, c->stream));
     HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, g_first, g_last);
     HF_LAUNCH_CHECK(c);
-    unsigned long long grid = (ng + S3_TEAMS - 1) / S3_TEAMS;
+    unsigned long long grid = (ng + S4_WARPS - 1) / S4_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    if (use_sync3()) {
-        HF_PROF(c, "dec_regroup_kernel");
-        dec_regroup_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
-        HF_LAUNCH_CHECK(c);
-    } else {
-        grid = (ng + S4_WARPS - 1) / S4_WARPS;
-        if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-        HF_PROF(c, "dec_regroup4_kernel");
-        dec_regroup4_kernel<<<(unsigned)grid, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
-        HF_LAUNCH_CHECK(c);
-    }
+    HF_PROF(c, "dec_regroup4_kernel");
+    dec_regroup4_kernel<<<(unsigned)grid, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
+    HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dec_verify_kernel"); dec_verify_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, c->stream>>>(d_tab, work, nch, g_first, g_last);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
@@ -1455,8 +1006,6 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
                  unsigned long long c0, unsigned long long c1, bool tail_only)
 {
     if (!c->smem_attr[ATTR_SYNC]) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_sync3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
-        HF_CUDA(c, cudaFuncSetAttribute(dec_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM));
         HF_CUDA(c, cudaFuncSetAttribute(dec_regroup4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM));
         c->smem_attr[ATTR_SYNC] = true;
@@ -1471,20 +1020,11 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
         ngroups = (c1 + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
         if (ngroups <= g_first) return HF_OK;
     }
-    if (!use_sync3()) {
-        unsigned long long grid4 = (ngroups - g_first + S4_WARPS - 1) / S4_WARPS;
-        if (grid4 > (unsigned long long)c->sm_count) grid4 = c->sm_count;
-        HF_PROF(c, "dec_sync4_kernel");
-        dec_sync4_kernel<<<(unsigned)grid4, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
-                                                                            g_first, ngroups, tail_only ? 1u : 0u);
-        HF_LAUNCH_CHECK(c);
-        return HF_OK;
-    }
-    unsigned long long grid = (ngroups - g_first + S3_TEAMS - 1) / S3_TEAMS;
-    if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    HF_PROF(c, "dec_sync3_kernel");
-    dec_sync3_kernel<<<(unsigned)grid, S3_THREADS, S3_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
-                                                                       g_first, ngroups, tail_only ? 1u : 0u);
+    unsigned long long grid4 = (ngroups - g_first + S4_WARPS - 1) / S4_WARPS;
+    if (grid4 > (unsigned long long)c->sm_count) grid4 = c->sm_count;
+    HF_PROF(c, "dec_sync4_kernel");
+    dec_sync4_kernel<<<(unsigned)grid4, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
+                                                                        g_first, ngroups, tail_only ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -1495,8 +1035,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
 {
     if (c1 <= c0) return HF_OK;
     if (!c->smem_attr[ATTR_WRITE]) {
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
-        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3L_SMEM));
+        HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         c->smem_attr[ATTR_WRITE] = true;
     }
     // units per run: a whole chunk per warp when that still gives every warp of the machine 16 runs or more (fewer
@@ -1506,15 +1045,8 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     const unsigned long long nruns = (c1 - c0) * ((DEC_THREADS / 32) / upw);
     unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
-    static int use_lut = -1;
-    if (use_lut < 0) { const char *e = getenv("HF_WRITE"); use_lut = (e && e[0] == '4') ? 1 : 0; }    // development switch (A/B timing)
-    if (use_lut) {
-        HF_PROF(c, "dec_write4_kernel");
-        dec_write3_kernel<true><<<(unsigned)grid, W3_THREADS, W3L_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
-    } else {
-        HF_PROF(c, "dec_write3_kernel");
-        dec_write3_kernel<false><<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
-    }
+    HF_PROF(c, "dec_write3_kernel");
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -1,5 +1,5 @@
 // decode_common.cuh — bit readers and the table walk shared by the exact decoder (decode.cu) and the
-// single-pass decoder (decode_fast.cu).  Private to libhuffb200.
+// word-walk kernels (decode2.cu).  Private to libhuffb200.
 #pragma once
 #include "common.cuh"
 
@@ -38,14 +38,8 @@ __device__ __forceinline__ unsigned long long peek64(const F &f, uint32_t bitpos
 constexpr int DEC_THREADS = 512;
 constexpr uint32_t SUB_BITS = 256;                              // bits per subsequence (thread)
 constexpr uint32_t CHUNK_BITS = DEC_THREADS * SUB_BITS;         // 131072 bits = 16 KiB
-// the synchronisation kernel's unit of convergence: a team of DEC_TEAM_THREADS threads, DEC_SPAN_SUBS subsequences each
-#ifndef HF_TEAM_THREADS
-#define HF_TEAM_THREADS 128
-#endif
-constexpr int DEC_TEAM_THREADS = HF_TEAM_THREADS;
-constexpr uint32_t DEC_SPAN_SUBS = 4;
-constexpr uint32_t GROUP_CHUNKS = DEC_TEAM_THREADS * DEC_SPAN_SUBS / DEC_THREADS;   // 1
-static_assert(GROUP_CHUNKS >= 1 && GROUP_CHUNKS * DEC_THREADS == DEC_TEAM_THREADS * DEC_SPAN_SUBS, "a group is whole chunks");
+// the synchronisation kernel's unit of convergence (a "group"): one chunk, converged on by one warp (decode2.cu)
+constexpr uint32_t GROUP_CHUNKS = 1;
 // a speculative range call (hf_range_overflow) works on the last TAIL_CHUNKS chunks of the range, from a group boundary
 constexpr unsigned long long TAIL_CHUNKS = 16;
 __host__ __device__ inline unsigned long long tail_first_chunk(unsigned long long nch)
