@@ -205,9 +205,71 @@ KERNEL_BYTES = {
     "hist_smem_kernel": lambda n, c: n,
     "enc_bits_kernel": lambda n, c: n,
     "encode2_kernel": lambda n, c: n + c,
-    "dec_sync3_kernel": lambda n, c: c,
+    "dec_sync4_kernel": lambda n, c: c,
     "dec_write3_kernel": lambda n, c: c + n,
 }
+
+
+def reference_gpu_leg(n_bytes=1 << 30):
+    """the UNMODIFIED reference GPU compressor (oracle/_ref/ref_archive_gpu = Compressor.cu built for
+    sm_100a) on config 4's 1 GiB Zipf stream, in the same run: its own three timers (C:356-399, h:780-782, C:492-593;
+    PCIe copies, mallocs and the file write are inside them) and the wall time of the program.  Its extract is a
+    host program (1 core), timed by the CPU legs.  None when the binary did not travel."""
+    import re
+    from oracle import oracle as O
+    from huffman_b200 import synth
+    exe = O.ref_binary("ref_archive_gpu")
+    if not exe:
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "zipf.bin")
+        synth.zipf1g(n_bytes, device="cuda").cpu().numpy().tofile(p)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, p], cwd=td, capture_output=True, text=True, timeout=600)
+        wall = time.perf_counter() - t0
+        out_bytes = os.path.getsize(p + ".compressed") if os.path.exists(p + ".compressed") else 0
+    if r.returncode != 0 or not out_bytes:
+        return {"error": f"rc {r.returncode}", "stdout_tail": r.stdout[-200:]}
+    t = {m.group(1): float(m.group(2)) for m in re.finditer(r"(Histograming|Encoding) took ([0-9.eE+-]+) ms", r.stdout)}
+    m = re.search(r"construction time: ([0-9.]+) ms", r.stdout)
+    cons = float(m.group(1)) if m else None
+    tot = sum(v for v in (t.get("Histograming"), cons, t.get("Encoding")) if v)
+    return {"workload": "zipf1g", "bytes": n_bytes, "compressed_bytes": out_bytes, "wall_s": wall,
+            "histograming_ms": t.get("Histograming"), "construction_ms": cons, "encoding_ms": t.get("Encoding"),
+            "encode_gbs_by_its_timers": n_bytes / (tot * 1e-3) / 1e9 if tot else None,
+            "encode_gbs_wall": n_bytes / wall / 1e9,
+            "note": "unmodified Compressor.cu + gpuHuffmanConstruction.h, nvcc -arch sm_100a; timers include H2D, mallocs, D2H + fwrite"}
+
+
+def identity_check(args, codec, job, n_total, world, rank, dev):
+    """N > 1: the slices of the ranks, gathered on rank 0, must be BYTE-IDENTICAL to the single-GPU image of the same
+    stream (which the tests pin to the oracle and the reference): checked on the first GiB of the workload, sharded over
+    all ranks exactly as the timed job is."""
+    import torch
+    import torch.distributed as dist
+    from huffman_b200.sharded import shard_bounds
+    m = min(n_total, 1 << 30)
+    lo, hi = shard_bounds(m, world)[rank]
+    piece = make_chunk(args.workload, n_total, lo, hi, dev)
+    sl = job.compress(piece, m, 0)
+    image = torch.zeros(sl.image_bytes + 64, dtype=torch.uint8, device=dev) if rank == 0 else torch.zeros(16, dtype=torch.uint8, device=dev)
+    codec.gather_image_to_rank0(sl.buf, sl.first_byte, sl.range_bytes, image)
+    codec.sync()
+    same = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        whole = make_chunk(args.workload, n_total, 0, m, dev)
+        single = Codec_single(codec, whole)
+        same[0] = int(single.numel() == sl.image_bytes and bool(torch.equal(single, image[:sl.image_bytes])))
+        del whole, single
+    dist.broadcast(same, 0)
+    del image, piece
+    assert int(same.item()) == 1, "sharded image differs from the single-GPU image"
+    return {"bytes": m, "byte_identical_to_single_gpu": True}
+
+
+def Codec_single(codec, data):
+    """the single-GPU image of `data` (hf_compress on this context: no communicator involved)"""
+    return codec.compress(data)
 
 
 def run_ours(args):
@@ -232,7 +294,10 @@ def run_ours(args):
     chunk = make_chunk(args.workload, n_total, lo, hi, dev)
     n_shard = hi - lo
     codec = Codec(local)
+    if world > 1:
+        codec.comm_init()               # NCCL communicator inside the context: hf_compress_sharded / hf_decompress_sharded
     job = ShardedCodec(codec) if world > 1 else None
+    identity = identity_check(args, codec, job, n_total, world, rank, dev) if world > 1 else None
 
     out_img = torch.empty(codec.compress_bound(n_shard) + 4096, dtype=torch.uint8, device=dev)
     out_dec = torch.empty(n_shard + 64, dtype=torch.uint8, device=dev)
@@ -282,6 +347,7 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     codec.profile(True)
     launches0 = codec.launch_count()
+    coll0 = codec.collective_count()
     barrier()
     sampler.start()
     ev[0].record()
@@ -293,6 +359,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     launches = codec.launch_count() - launches0
+    collectives_per_step = (codec.collective_count() - coll0) // args.steps if job else 0
     prof = codec.profile_read()
     codec.profile(False)
     t_total = ev[0].elapsed_time(ev[-1])
@@ -335,6 +402,8 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"]}
+    if roof:
+        roof["traffic_source"] = "profiles/ncu_traffic.json: dram bytes per input byte from the round's ncu --set full capture, scaled to this shard (not measured in this run)" if roof["traffic"] is not None else None
     phases = {"encode": {"gbs_alg": (2 * n_total + c_total) * k / (t_enc * 1e-3) / 1e9},
               "decode": {"gbs_alg": (n_total + c_total) * k / (t_dec * 1e-3) / 1e9}}
     for p in phases.values():
@@ -364,7 +433,7 @@ def run_ours(args):
         ti_dec = sum(evi[2 * i + 1].elapsed_time(evi[2 * i + 2]) for i in range(args.steps))
         indexed = {"value": 2 * n_total * k / ((ti_enc + ti_dec) * 1e-3) / 1e9, "unit": UNIT,
                    "encode_gbs": n_total * k / (ti_enc * 1e-3) / 1e9, "decode_gbs": n_total * k / (ti_dec * 1e-3) / 1e9,
-                   "index_bytes": int(idx_i.numel()), "synchronisation_pass_skipped": "dec_sync3_kernel" not in prof_i,
+                   "index_bytes": int(idx_i.numel()), "synchronisation_pass_skipped": not any(kn.startswith("dec_sync") for kn in prof_i),
                    "enc_index_kernel_ms": prof_i.get("enc_index_kernel", (1, 0.0))[1] / max(prof_i.get("enc_index_kernel", (1, 0.0))[0], 1)}
         del index_buf
 
@@ -384,6 +453,13 @@ def run_ours(args):
                "encode_gbs": sample.size / tc / 1e9, "decode_gbs": sample.size / tdx / 1e9,
                "host_cores_available": os.cpu_count()}
 
+    refgpu = None
+    if rank == 0 and world == 1 and not args.no_refgpu:
+        try:
+            refgpu = reference_gpu_leg()
+        except Exception as e:                      # a baseline beside the number, never a reason to lose the number
+            refgpu = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": args.warmup,
@@ -392,10 +468,14 @@ def run_ours(args):
             "config": {"workload": args.workload, "bytes": n_total, "compressed_bytes": c_total,
                        "sharding": f"contiguous chunks x{world}", "l2": "inputs >> 126 MB L2, no flush needed",
                        "step": "full compress then full decompress of the stream"},
-            "encode_gbs": enc_gbs, "decode_gbs": dec_gbs, "phases": phases,
+            "encode_gbs": enc_gbs, "decode_gbs": dec_gbs, "encode_frac": phases["encode"]["frac"],
+            "decode_frac": phases["decode"]["frac"], "phases": phases,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "with_side_index": indexed,
+            "reference_gpu": refgpu, "identity": identity,
+            "parity_note": "byte identity is pinned by tests/ (oracle + the reference GPU binary's hashes, <= 256 MiB) and, at N > 1, by `identity` "
+                           "(first GiB against the single-GPU image); at the full size the bench asserts the round trip: the reference is undefined >= 2 GiB (bC:74-76)",
             "gpu_launches": launches, "clocks": clocks,
-            "collectives_per_step": (job.collectives // (k + args.warmup + 0)) if job else 0,
+            "collectives_per_step": collectives_per_step, "host_syncs_per_step": 2,
         }
         print(json.dumps(line), flush=True)
     codec.close()
@@ -483,6 +563,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-index", action="store_true")
+    ap.add_argument("--no-refgpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -36,6 +36,29 @@ class HeaderInfo(ctypes.Structure):
                 ("status", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class SliceInfo(ctypes.Structure):          # hf_slice_info_t
+    _fields_ = [("first_byte", ctypes.c_uint64), ("range_bytes", ctypes.c_uint64), ("start_bit", ctypes.c_uint64),
+                ("end_bit", ctypes.c_uint64), ("image_bytes", ctypes.c_uint64), ("n_total", ctypes.c_uint64),
+                ("needed_capacity", ctypes.c_uint64)]
+
+
+class ShardOut(ctypes.Structure):           # hf_shard_out_t
+    _fields_ = [("n_total", ctypes.c_uint64), ("out_offset", ctypes.c_uint64), ("out_bytes", ctypes.c_uint64),
+                ("payload_start_bit", ctypes.c_uint64), ("needed_symbols", ctypes.c_uint64),
+                ("max_code_bits", ctypes.c_uint32), ("is_odd", ctypes.c_uint32), ("last_byte", ctypes.c_uint32),
+                ("status", ctypes.c_uint32)]
+
+
+class UniqueId(ctypes.Structure):           # hf_unique_id_t (an ncclUniqueId)
+    _fields_ = [("internal", ctypes.c_char * 128)]
+
+
+SHARD_HALO = 32
+SHARD_REC_BYTES = 48
+SHARD_MAX_RANKS = 64
+HEADER_MAX = 720928
+
+
 class KernelTime(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 48), ("launches", ctypes.c_uint32), ("total_ms", ctypes.c_float)]
 
@@ -54,7 +77,6 @@ _SIGS = {
     "hf_profile_enable": (ctypes.c_int, [_P, ctypes.c_int]),
     "hf_profile_read": (ctypes.c_int, [_P, ctypes.POINTER(KernelTime), ctypes.c_uint32,
                                        ctypes.POINTER(ctypes.c_uint32)]),
-    "hf_debug_read_ws": (ctypes.c_int, [_P, _U64, _P, _U64]),
     "hf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t]),
     "hf_host_free": (ctypes.c_int, [_P]),
     "hf_codebook_bytes": (ctypes.c_size_t, []),
@@ -73,7 +95,6 @@ _SIGS = {
     "hf_decode": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P]),
     "hf_range_overflow": (ctypes.c_int, [_P, _P, _U64, _U64, _P, _P]),
     "hf_decode_range": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _P, _U64, _P]),
-    "hf_set_decode_mode": (ctypes.c_int, [_P, ctypes.c_int]),
     "hf_decompress": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_index_bound": (_U64, [_U64]),
     "hf_compress_indexed": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64), _P, _U64, ctypes.POINTER(_U64)]),
@@ -81,6 +102,21 @@ _SIGS = {
     "hf_compress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
     "hf_decompressed_size_host": (ctypes.c_int, [_P, _U64, ctypes.POINTER(_U64)]),
     "hf_decompress_host": (ctypes.c_int, [_P, _P, _U64, _P, _U64, ctypes.POINTER(_U64)]),
+    "hf_comm_unique_id": (ctypes.c_int, [ctypes.POINTER(UniqueId)]),
+    "hf_comm_init": (ctypes.c_int, [_P, ctypes.POINTER(UniqueId), ctypes.c_int, ctypes.c_int]),
+    "hf_comm_destroy": (ctypes.c_int, [_P]),
+    "hf_collective_count": (_U64, [_P]),
+    "hf_compress_sharded": (ctypes.c_int, [_P, _P, _U64, _U64, ctypes.c_uint32, _P, _U64, ctypes.POINTER(SliceInfo)]),
+    "hf_decompress_sharded": (ctypes.c_int, [_P, _P, _U64, _U64, _U64, _P, _U64, ctypes.POINTER(ShardOut)]),
+    "hf_gather_image": (ctypes.c_int, [_P, _P, _U64, _U64, _P, _U64]),
+    "hf_shard_compress_local": (ctypes.c_int, [_P, _P, _U64, _P]),
+    "hf_shard_compress_bits": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _U64, _P]),
+    "hf_shard_compress_pack": (ctypes.c_int, [_P, _P, _U64, _U64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, _P, _P, _U64, _P]),
+    "hf_shard_compress_seams": (ctypes.c_int, [_P, _U64, ctypes.c_int, ctypes.c_int, _P, _P, _P, ctypes.POINTER(SliceInfo)]),
+    "hf_shard_decompress_header": (ctypes.c_int, [_P, ctypes.c_int, _P, _U64, _P]),
+    "hf_shard_decompress_sync": (ctypes.c_int, [_P, ctypes.c_int, _P, _U64, _P, _U64, _U64, _P]),
+    "hf_shard_decompress_write": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, _P, _U64, _U64, _P, _U64, _P]),
+    "hf_shard_decompress_finish": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, _P, ctypes.POINTER(ShardOut)]),
     "hf_archive_file": (ctypes.c_int, [_P, ctypes.c_char_p]),
     "hf_extract_file": (ctypes.c_int, [_P, ctypes.c_char_p]),
 }

@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CbInfo, HeaderInfo, HuffmanError, KernelTime, NSYM
+from ._lib import CbInfo, HeaderInfo, HuffmanError, KernelTime, NSYM, ShardOut, SliceInfo, UniqueId
 
 
 def _ptr(t):
@@ -187,10 +187,6 @@ class Codec:
                                              _ptr(out), out.numel() // 2, _ptr(result)))
         return result
 
-    def set_decode_mode(self, exact_only):
-        """True: always the exact multi-pass decoder; False (default): single pass with on-device fallback"""
-        self._check(self.lib.hf_set_decode_mode(self.ctx, 1 if exact_only else 0))
-
     def codebook_info(self, cb):
         return cb.info()
 
@@ -206,6 +202,45 @@ class Codec:
         self._check(self.lib.hf_decompress(self.ctx, _ptr(image), image.numel(), _ptr(out), out.numel(),
                                            ctypes.byref(size)))
         return out[: size.value]
+
+    # ---- sharded job: one stream over several GPUs (hf_comm_*, hf_compress_sharded, hf_decompress_sharded) ----
+    has_comm = False
+
+    def comm_init(self, group=None):
+        """NCCL communicator of this context over the ranks of a torch.distributed group: rank 0 creates the id,
+        torch broadcasts its 128 bytes (any backend), every rank calls hf_comm_init.  torch is the bootstrap only:
+        the collectives of the data path are issued by the library on this context's stream."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = UniqueId()
+        if rank == 0:
+            self._check(self.lib.hf_comm_unique_id(ctypes.byref(uid)))
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        self._check(self.lib.hf_comm_init(self.ctx, ctypes.byref(uid), rank, world))
+        self.has_comm, self.rank, self.world = True, rank, world
+
+    def collective_count(self):
+        return int(self.lib.hf_collective_count(self.ctx))
+
+    def compress_sharded(self, chunk, n_total, last_byte, out):
+        """this rank's chunk -> its slice of the single image in `out` (16-byte aligned); returns SliceInfo"""
+        info = SliceInfo()
+        self._check(self.lib.hf_compress_sharded(self.ctx, _ptr(chunk), chunk.numel(), n_total, last_byte, _ptr(out),
+                                                 out.numel(), ctypes.byref(info)))
+        return info
+
+    def decompress_sharded(self, buf, range_bytes, halo_bytes, image_bytes, out):
+        res = ShardOut()
+        self._check(self.lib.hf_decompress_sharded(self.ctx, _ptr(buf), range_bytes, halo_bytes, image_bytes, _ptr(out),
+                                                   out.numel(), ctypes.byref(res)))
+        return res
+
+    def gather_image_to_rank0(self, buf, first_byte, range_bytes, image):
+        self._check(self.lib.hf_gather_image(self.ctx, _ptr(buf), first_byte, range_bytes, _ptr(image), image.numel()))
 
     # ---- host buffers (the end-to-end path the programs use) ----
     def compress_host(self, h_in, h_out=None):

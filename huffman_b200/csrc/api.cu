@@ -105,7 +105,7 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     c->sm_count = prop.multiProcessorCount;
     c->stream = (cudaStream_t)stream;                   // NULL = the legacy default stream, as the reference uses
     c->own_stream = false;
-    c->decode_exact_only = true;                        // see hf_set_decode_mode
+    c->nranks = 1;
     bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_pipe, PIPE_SLOTS * 8) == cudaSuccess;
@@ -131,6 +131,7 @@ int hf_ctx_destroy(hf_ctx *ctx)
     if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
     if (c->h_pipe) cudaFreeHost(c->h_pipe);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    shard_release(c);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->d_in) cudaFree(c->d_in);
@@ -207,17 +208,6 @@ int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *
     }
     *n_out = n;
     c->prof_n = 0;
-    return HF_OK;
-}
-
-// development aid: copies `bytes` of the context's workspace at byte offset `off` to the host (timing builds)
-int hf_debug_read_ws(hf_ctx *ctx, uint64_t off, void *h_dst, uint64_t bytes)
-{
-    NEED_CTX(ctx);
-    Ctx *c = CTX(ctx);
-    if (!c->ws || off + bytes > c->ws_bytes) return set_err(c, HF_ERR_ARG, "hf_debug_read_ws: out of range");
-    HF_CUDA(c, cudaStreamSynchronize(c->stream));
-    HF_CUDA(c, cudaMemcpy(h_dst, (uint8_t *)c->ws + off, bytes, cudaMemcpyDeviceToHost));
     return HF_OK;
 }
 
@@ -303,7 +293,7 @@ int hf_header_pack(hf_ctx *ctx, const void *d_codebook, uint64_t n_bytes, uint32
     if (capacity < 4 + 11 * u + 8 + 4)
         return set_err(c, HF_ERR_CAPACITY, "hf_header_pack: capacity %llu below the header bound %llu",
                        (unsigned long long)capacity, (unsigned long long)(4 + 11 * u + 12));
-    return launch_header_pack(c, reinterpret_cast<const Codebook *>(d_codebook), n_bytes, last_byte, d_file, capacity);
+    return launch_header_pack(c, reinterpret_cast<const Codebook *>(d_codebook), n_bytes, last_byte, nullptr, d_file, capacity, nullptr);
 }
 
 int hf_encode(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, const void *d_codebook, uint8_t *d_stream,
@@ -311,7 +301,7 @@ int hf_encode(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, const void *d_
 {
     NEED_CTX(ctx);
     if ((!d_in && n_bytes) || !d_codebook || !d_stream) return set_err(CTX(ctx), HF_ERR_ARG, "hf_encode: null pointer");
-    return launch_encode(CTX(ctx), d_in, n_bytes, reinterpret_cast<const Codebook *>(d_codebook), d_stream, start_bit, 0);
+    return launch_encode(CTX(ctx), d_in, n_bytes, reinterpret_cast<const Codebook *>(d_codebook), d_stream, start_bit, nullptr);
 }
 
 // the side index object: this header, then n_subs u16 records (encode2.cu enc_index_kernel)
@@ -325,7 +315,8 @@ struct IndexHeader {
 static_assert(sizeof(IndexHeader) == 64, "index header is 64 bytes");
 static const uint32_t INDEX_MAGIC = 0x58494648u;
 
-// shared tail of hf_compress / hf_compress_host: codebook -> sizes -> header -> payload [-> side index].
+// hf_compress_indexed: codebook -> sizes -> header -> payload -> side index.  The index needs the stream's geometry on the
+// host, so this variant learns the sizes before it packs (hf_compress does not: compress_async below).
 // *h_last is read after the synchronisation inside hf_codebook_info.
 static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *h_last, uint8_t *d_file,
                                uint64_t capacity, uint64_t *h_file_bytes, uint8_t *d_index = nullptr,
@@ -347,8 +338,7 @@ static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const ui
                        (unsigned long long)capacity);
     rc = hf_header_pack(ctx, cb, n, (n & 1) ? *h_last : 0, d_file, capacity);
     if (rc) return rc;
-    rc = launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64,
-                       info.max_code_bits ? info.max_code_bits : 1);
+    rc = launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64, nullptr);
     if (rc || !d_index) return rc;
     // the side index: records for exactly the stream just packed, at this image's alignment
     if (h_index_bytes) *h_index_bytes = 0;
@@ -372,22 +362,49 @@ static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const ui
     return HF_OK;
 }
 
+// hf_compress / hf_compress_host after the histogram: codebook -> plan (sizes, start bit, capacity check: all on the
+// device) -> header -> payload; nothing waits for the host.  d_last / last_byte: see launch_header_pack.
+static int compress_async(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_last, uint32_t last_byte, uint8_t *d_file,
+                          uint64_t capacity, ShardPlan **d_plan)
+{
+    Codebook *cb = reinterpret_cast<Codebook *>(c->d_cb);
+    int rc = launch_codebook(c, reinterpret_cast<unsigned long long *>(c->d_hist), cb);
+    if (rc) return rc;
+    rc = launch_plan_single(c, cb, n, capacity, d_plan);
+    if (rc) return rc;
+    rc = launch_header_pack(c, cb, n, last_byte, (n & 1) ? d_last : nullptr, d_file, capacity, *d_plan);
+    if (rc) return rc;
+    return launch_encode(c, d_in, n, cb, d_file, 0, *d_plan);
+}
+
+// the plan after the stream has drained: the image size, or why there is no image
+static int compress_result(Ctx *c, const ShardPlan *d_plan, uint64_t capacity, uint64_t *h_file_bytes)
+{
+    ShardPlan *h = reinterpret_cast<ShardPlan *>((uint8_t *)c->h_scratch + 2560);
+    HF_CUDA(c, cudaMemcpyAsync(h, d_plan, sizeof(ShardPlan), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h_file_bytes) *h_file_bytes = h->image_bytes;
+    if (h->status == HF_ERR_CAPACITY)
+        return set_err(c, HF_ERR_CAPACITY, "hf_compress: need %llu bytes, capacity %llu", (unsigned long long)h->image_bytes,
+                       (unsigned long long)capacity);
+    if (h->status) return set_err(c, (int)h->status, "codebook: a code word is longer than 64 bits");
+    return HF_OK;
+}
+
 int hf_compress(hf_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_file, uint64_t capacity,
                 uint64_t *h_file_bytes)
 {
     NEED_CTX(ctx);
     Ctx *c = CTX(ctx);
     if ((!d_in && n) || !d_file) return set_err(c, HF_ERR_ARG, "hf_compress: null pointer");
+    if (capacity < 12) return set_err(c, HF_ERR_CAPACITY, "hf_compress: capacity %llu is below any image", (unsigned long long)capacity);
     HF_CUDA(c, cudaMemsetAsync(c->d_hist, 0, NSYM * 8, c->stream));
     int rc = launch_histogram(c, d_in, n, reinterpret_cast<unsigned long long *>(c->d_hist));
     if (rc) return rc;
-    uint8_t *h_last = reinterpret_cast<uint8_t *>(c->h_scratch) + 2048;
-    *h_last = 0;
-    if (n & 1) HF_CUDA(c, cudaMemcpyAsync(h_last, d_in + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
-    rc = compress_after_hist(c, d_in, n, h_last, d_file, capacity, h_file_bytes);
+    ShardPlan *d_plan = nullptr;
+    rc = compress_async(c, d_in, n, n ? d_in + n - 1 : nullptr, 0, d_file, capacity, &d_plan);
     if (rc) return rc;
-    HF_CUDA(c, cudaStreamSynchronize(c->stream));
-    return HF_OK;
+    return compress_result(c, d_plan, capacity, h_file_bytes);
 }
 
 uint64_t hf_index_bound(uint64_t n)
@@ -478,18 +495,11 @@ int hf_range_overflow(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes,
                                reinterpret_cast<unsigned long long *>(d_result));
 }
 
-int hf_set_decode_mode(hf_ctx *ctx, int exact_only)
-{
-    NEED_CTX(ctx);
-    CTX(ctx)->decode_exact_only = exact_only != 0;
-    return HF_OK;
-}
-
-// what the decode kernels report (decode.cu: DecWork = result[4], flags[4]) sits at ws + 8 MiB
+// what the decode kernels report (DecWork, decode_common.cuh) sits at the start of the workspace's stage region
 static int check_decode_flags(Ctx *c)
 {
     unsigned long long *h = reinterpret_cast<unsigned long long *>((uint8_t *)c->h_scratch + 3072);
-    HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + (8u << 20), 64, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + WS_STAGE_OFFSET, 64, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (h[4 + 1]) return set_err(c, HF_ERR_FORMAT, "hf_decode: the payload holds bits that are no code word");
     return HF_OK;
@@ -500,22 +510,30 @@ int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8
 {
     NEED_CTX(ctx);
     Ctx *c = CTX(ctx);
-    hf_header_info_t info;
-    int rc = hf_parse_header(ctx, d_file, file_bytes, c->d_tab, &info);
+    if (!d_file) return set_err(c, HF_ERR_ARG, "hf_decompress: null pointer");
+    if (file_bytes < 11) return set_err(c, HF_ERR_FORMAT, "hf_decompress: %llu bytes is shorter than any image",
+                                        (unsigned long long)file_bytes);
+    if (!d_out) capacity = 0;
+    hf_header_info_t *d_info = reinterpret_cast<hf_header_info_t *>((uint8_t *)c->d_hist + NSYM * 8);
+    DecodeTable *tab = reinterpret_cast<DecodeTable *>(c->d_tab);
+    int rc = launch_parse_header(c, d_file, file_bytes, tab, d_info);
     if (rc) return rc;
-    if (h_out_bytes) *h_out_bytes = info.original_bytes;
-    if (info.original_bytes > capacity)
-        return set_err(c, HF_ERR_CAPACITY, "hf_decompress: need %llu bytes, capacity %llu",
-                       (unsigned long long)info.original_bytes, (unsigned long long)capacity);
-    if (info.original_bytes && !d_out) return set_err(c, HF_ERR_ARG, "hf_decompress: null output");
-    const uint64_t nsym = info.original_bytes / 2;
-    if (nsym) {
-        rc = launch_decode(c, d_file, file_bytes, info.payload_start_bit, nsym, reinterpret_cast<DecodeTable *>(c->d_tab), d_out);
-        if (rc) return rc;
-    }
-    if (info.is_odd) HF_CUDA(c, cudaMemsetAsync(d_out + info.original_bytes - 1, (int)info.last_byte, 1, c->stream));   // D:286-289
-    if (nsym) return check_decode_flags(c);
+    rc = launch_decompress_image(c, d_file, file_bytes, d_info, tab, d_out, capacity);
+    if (rc) return rc;
+    // the one synchronisation: what the header said, what the kernels flagged
+    hf_header_info_t *h = reinterpret_cast<hf_header_info_t *>((uint8_t *)c->h_scratch + 1024);
+    uint32_t *h_tab = reinterpret_cast<uint32_t *>((uint8_t *)c->h_scratch + 1536);
+    unsigned long long *h_work = reinterpret_cast<unsigned long long *>((uint8_t *)c->h_scratch + 3072);
+    HF_CUDA(c, cudaMemcpyAsync(h, d_info, sizeof(hf_header_info_t), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaMemcpyAsync(h_tab, tab, 48, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(c, cudaMemcpyAsync(h_work, (uint8_t *)c->ws + WS_STAGE_OFFSET, 64, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h->status || h_tab[6]) return set_err(c, HF_ERR_FORMAT, "hf_decompress: malformed header");
+    if (h_out_bytes) *h_out_bytes = h->original_bytes;
+    if (h_work[4 + 2])
+        return set_err(c, d_out ? HF_ERR_CAPACITY : HF_ERR_ARG, "hf_decompress: need %llu bytes, capacity %llu",
+                       (unsigned long long)h->original_bytes, (unsigned long long)capacity);
+    if (h_work[4 + 1]) return set_err(c, HF_ERR_FORMAT, "hf_decode: the payload holds bits that are no code word");
     return HF_OK;
 }
 
@@ -595,7 +613,10 @@ int hf_compress_host(hf_ctx *ctx, const uint8_t *h_in, uint64_t n, uint8_t *h_fi
         if (rc) return rc;
     }
     uint64_t total = 0;
-    rc = compress_after_hist(c, d_in, n, n ? h_in + n - 1 : nullptr, d_file, bound, &total);
+    ShardPlan *d_plan = nullptr;
+    rc = compress_async(c, d_in, n, nullptr, (n & 1) ? h_in[n - 1] : 0u, d_file, bound, &d_plan);
+    if (rc) return rc;
+    rc = compress_result(c, d_plan, bound, &total);
     if (h_file_bytes) *h_file_bytes = total;
     if (rc) return rc;
     if (total > capacity)

@@ -43,6 +43,7 @@ struct CbWork {
 };
 
 size_t cb_work_bytes() { return sizeof(CbWork); }
+static_assert(sizeof(CbWork) <= WS_SCRATCH_BYTES, "CbWork lives in the workspace's scratch region");
 
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *warp_sums, uint32_t *total)
@@ -288,7 +289,6 @@ __global__ void cb_codes_kernel(const unsigned long long *__restrict__ hist, CbW
         if (len > 64) { atomicExch(&cb->status, (uint32_t)HF_ERR_CODE_TOO_LONG); len = 64; }
         cb->len[sym] = (uint8_t)len;
         cb->code[sym] = code;
-        cb->enc32[sym] = len <= ENC32_MAX_LEN ? ((len << 27) | (uint32_t)code) : 0xFFFFFFFFu;
         const uint32_t v24 = len <= 23 ? ((1u << len) | (uint32_t)code) : 0u;
         const uint32_t fsym = sym ^ (sym >> 8);                 // the encoder's bank-spreading index (encode.cu fold16)
         cb->p16[fsym] = (uint16_t)v24;
@@ -363,8 +363,11 @@ __device__ __forceinline__ void or_bits(uint32_t *words, unsigned long long bitp
 }
 
 __global__ void header_pack_kernel(const Codebook *__restrict__ cb, const uint32_t *__restrict__ entry_off,
-                                   uint64_t n_bytes, uint32_t last_byte, uint8_t *d_file)
+                                   uint64_t n_bytes, uint32_t last_byte, const uint8_t *__restrict__ d_last, uint8_t *d_file,
+                                   const ShardPlan *__restrict__ plan)
 {
+    if (plan && plan->status) return;                   // the image does not fit (or the codebook is unusable)
+    if (d_last) last_byte = *d_last;
     uint32_t *words = reinterpret_cast<uint32_t *>((uintptr_t)d_file & ~(uintptr_t)3);
     const unsigned long long file_bit0 = ((uintptr_t)d_file & 3) * 8;
     const uint32_t pre = 3 + (uint32_t)(n_bytes & 1);
@@ -431,8 +434,8 @@ int launch_shard_bits(Ctx *c, const unsigned long long *d_hist, const Codebook *
     return HF_OK;
 }
 
-int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t last_byte,
-                       uint8_t *d_file, uint64_t capacity)
+int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t last_byte, const uint8_t *d_last,
+                       uint8_t *d_file, uint64_t capacity, const ShardPlan *plan)
 {
     // worst-case header: 4 + 65536 * (24 + 64) / 8 + 8 bytes; zero what the capacity allows
     uint64_t bound = 4 + (uint64_t)NSYM * 11 + 8 + 8;
@@ -441,7 +444,7 @@ int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t 
                                       (unsigned long long)capacity);
     HF_CUDA(c, cudaMemsetAsync(d_file, 0, z, c->stream));
     HF_PROF(c, "header_pack_kernel"); header_pack_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_cb, entry_off_of(const_cast<Codebook *>(d_cb)),
-                                                         n_bytes, last_byte, d_file);
+                                                         n_bytes, last_byte, d_last, d_file, plan);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -19,8 +19,6 @@ namespace hf {
 constexpr uint32_t NSYM = HF_NSYM;
 
 // ---- device-resident codebook (hf_codebook_bytes) ---------------------------------
-// enc32: (len << 27) | code for len <= 26, the encoder's one-gather fast table.
-constexpr uint32_t ENC32_MAX_LEN = 26;
 struct Codebook {
     uint32_t U;
     uint32_t maxlen;
@@ -31,7 +29,6 @@ struct Codebook {
     unsigned long long pad1;
     uint16_t order[NSYM];      // rank -> symbol, ascending (count, symbol)
     uint8_t len[NSYM];         // by symbol, 0 when absent
-    uint32_t enc32[NSYM];      // by symbol
     unsigned long long code[NSYM];   // by symbol, right aligned, root->leaf
     // the encoder's shared-memory table: (1 << len) | code for 1 <= len <= 23 (0 = longer or absent),
     // low 16 bits in p16, high 8 bits in p8, both indexed by sym ^ (sym >> 8); contiguous and 16-byte
@@ -104,6 +101,21 @@ struct DecodeTable {
     alignas(16) uint32_t flat2[1u << FLAT_MAX];
 };
 
+// ---- where a slice of the image lies ---------------------------------------------------------------
+// Computed on the device (sharded.cu shard_plan_kernel) from the codebook's table size and the payload bit counts of
+// the ranks (one rank: the codebook's own payload_bits), so that neither the sizes nor the start bit visit the host
+// between the histogram and the last packed byte.  The stages that write the image return at once when status is set.
+struct ShardPlan {
+    unsigned long long start_bit, end_bit;      // global bits (from image byte 0) of this rank's payload slice
+    unsigned long long first_byte;              // global byte of the rank's buffer[0]
+    unsigned long long range_bytes;             // bytes the rank owns: the ranges of consecutive ranks tile the image
+    unsigned long long own_bytes;               // bytes the rank's encoder touches (range_bytes, or one more: the seam byte)
+    unsigned long long image_bytes;             // size of the whole image
+    unsigned long long local_start_bit;         // start_bit - 8 * first_byte: where the encoder starts in the rank's buffer
+    unsigned long long need_bytes;              // capacity this rank's buffer must have
+    unsigned long long status;                  // HF_OK, HF_ERR_CAPACITY, HF_ERR_CODE_TOO_LONG
+};
+
 // ---- context ----------------------------------------------------------------------
 struct Ctx {
     int device;
@@ -132,7 +144,11 @@ struct Ctx {
     // kernels whose dynamic shared-memory limit has been raised on THIS context's device (a process may hold
     // contexts on several GPUs; the attribute is per device)
     bool smem_attr[8];
-    bool decode_exact_only;         // hf_set_decode_mode: kept for ABI compatibility, the decoder has one (exact) mode
+    // sharded job (sharded.cu): NCCL communicator, device state, summed histogram, header staging
+    void *comm;
+    int rank, nranks;
+    uint64_t collectives;
+    void *d_shard, *d_hist2, *d_hdr;
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
     bool prof_open;                 // a begin event is pending
@@ -149,6 +165,16 @@ void prof_end(Ctx *c);
 
 int set_err(Ctx *c, int code, const char *fmt, ...);
 int ensure_ws(Ctx *c, size_t bytes);
+
+// The context's workspace (ctx->ws) is one allocation with two regions:
+//   [0, WS_SCRATCH_BYTES)   short-lived scratch of one stage at a time: the histogram's per-CTA partial bins
+//                           (hist.cu, sm_count x 128 KiB), the codebook builder's arrays (codebook.cu CbWork), the
+//                           table builder's source arrays (decode.cu TabSrc); each stage is done with it when the next
+//                           one starts (one stream);
+//   [WS_STAGE_OFFSET, ...)  what lives across the kernels of an encode (unit / group bit counts, encode2.cu Enc2Work)
+//                           or of a decode (DecWork + DecLayout, decode_common.cuh), sized by the input.
+constexpr size_t WS_SCRATCH_BYTES = 24u << 20;
+constexpr size_t WS_STAGE_OFFSET = WS_SCRATCH_BYTES;
 
 #define HF_CUDA(ctx, call)                                                              \
     do {                                                                                \
@@ -176,10 +202,12 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
 int launch_codebook(Ctx *c, const unsigned long long *d_hist, Codebook *d_cb);
 int launch_shard_bits(Ctx *c, const unsigned long long *d_hist, const Codebook *d_cb,
                       unsigned long long *d_bits);
-int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t last_byte,
-                       uint8_t *d_file, uint64_t capacity);
+// d_last: device address of the odd last input byte (its value is read on the device), or NULL: `last_byte` is it.
+// plan: NULL, or the device plan whose status gates the stage and whose local_start_bit replaces start_bit.
+int launch_header_pack(Ctx *c, const Codebook *d_cb, uint64_t n_bytes, uint32_t last_byte, const uint8_t *d_last,
+                       uint8_t *d_file, uint64_t capacity, const ShardPlan *plan);
 int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb,
-                  uint8_t *d_stream, uint64_t start_bit, uint32_t maxlen_hint);
+                  uint8_t *d_stream, uint64_t start_bit, const ShardPlan *plan);
 int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, const uint8_t *d_stream,
                         uint64_t start_bit, uint16_t *d_rec, uint64_t n_subs);
 int launch_parse_header(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, DecodeTable *d_tab,
@@ -205,6 +233,15 @@ uint64_t index_subs(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t sta
 int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, uint64_t first_bit,
                         bool tail_only, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
                         unsigned long long *d_result);
+int launch_range_sync(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, const DecodeTable *d_tab,
+                      unsigned long long *d_probe);
+int launch_range_write(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
+                       const unsigned long long *d_first_bit, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
+                       unsigned long long *d_result);
+int launch_plan_single(Ctx *c, const Codebook *d_cb, uint64_t n_total, uint64_t capacity, ShardPlan **d_plan);
+void shard_release(Ctx *c);
+int launch_decompress_image(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, const hf_header_info_t *d_info,
+                            const DecodeTable *d_tab, uint8_t *d_out, uint64_t capacity);
 
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__

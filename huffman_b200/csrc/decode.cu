@@ -39,6 +39,7 @@ struct TabSrc {                         // workspace arrays filled by the header
     uint32_t U;
     uint32_t pad;
 };
+static_assert(sizeof(TabSrc) <= WS_SCRATCH_BYTES, "TabSrc lives in the workspace's scratch region");
 
 __global__ void dt_from_codebook_kernel(const Codebook *__restrict__ cb, TabSrc *__restrict__ src)
 {
@@ -375,10 +376,11 @@ dec_scan3_kernel(DecWork *work, unsigned long long nch, unsigned long long c0, u
 }
 
 // U == 1 with a zero-length code: the payload is empty, every symbol is the same
-__global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned long long n_symbols,
+__global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, const DecWork *__restrict__ work,
                                 uint16_t *__restrict__ out)
 {
     if (!(tab->single_sym & 0x10000u)) return;
+    const unsigned long long n_symbols = work->start[1];
     const uint16_t s = (uint16_t)tab->single_sym;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -387,18 +389,49 @@ __global__ void dec_fill_kernel(const DecodeTable *__restrict__ tab, unsigned lo
 
 // -----------------------------------------------------------------------------------
 int launch_table_planes(Ctx *c, DecodeTable *d_tab);             // decode2.cu
-int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c0, unsigned long long c1, bool tail_only);
-int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+                 unsigned long long c0, unsigned long long c1, bool tail_only, bool speculative);
+int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, bool check);
+                  unsigned long long c1, uint16_t *out, bool check);
 int launch_idx_chunks(Ctx *c, DecWork *work, unsigned long long nch);
-int launch_idx_total(Ctx *c, DecWork *work, unsigned long long n_symbols);
-
-int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+int launch_idx_total(Ctx *c, DecWork *work);
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
                 unsigned long long c0, unsigned long long c1, bool speculative);
+int launch_fix_head(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
+                    const DecodeTable *d_tab, DecWork *work, unsigned long long nch);
+
+// where a decode starts and how much it may write (DecWork::start), from host values ...
+__global__ void dec_start_kernel(DecWork *work, unsigned long long F0, unsigned long long n_symbols)
+{
+    work->start[0] = F0;
+    work->start[1] = n_symbols;
+}
+
+// ... from a header parsed on the device (hf_decompress: nothing visits the host before the decode is enqueued).  A
+// malformed header or an output that does not fit decodes nothing: the first code word is put behind everything.
+__global__ void dec_start_info_kernel(DecWork *work, const hf_header_info_t *__restrict__ info,
+                                      const DecodeTable *__restrict__ tab, unsigned long long lead_bits,
+                                      unsigned long long capacity, uint8_t *d_out)
+{
+    const unsigned long long n = info->original_bytes;
+    bool ok = info->status == 0 && tab->status == 0;
+    if (ok && n > capacity) { work->flags[2] = 1; ok = false; }
+    work->start[0] = ok ? lead_bits + info->payload_start_bit : NO_START - 1;
+    work->start[1] = ok ? n / 2 : 0;
+    if (ok && info->is_odd) d_out[n - 1] = (uint8_t)info->last_byte;      // D:286-289
+}
+
+// ... from the hand-over bit of a sharded stream: *first_bit = bits from the range's first byte to its first code word
+// (the predecessor's overflow); a range no code word starts in keeps F0 at or behind its end
+__global__ void dec_start_range_kernel(DecWork *work, const unsigned long long *__restrict__ first_bit,
+                                       unsigned long long lead_bits, unsigned long long out_symbols)
+{
+    work->start[0] = lead_bits + *first_bit;
+    work->start[1] = out_symbols;
+}
 
 static int build_tables(Ctx *c, TabSrc *src, DecodeTable *d_tab)
 {
@@ -461,18 +494,18 @@ static int launch_scan(Ctx *c, DecWork *work, unsigned long long nch, unsigned l
 
 // The decode kernels over the chunks [c0, c1) of the frame: the whole stream in one go, or one slice of a pipelined
 // host-buffer decode (slices in ascending order; c0 a multiple of GROUP_CHUNKS).
-static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
-                               unsigned long long range_end_bit, uint64_t n_symbols, const DecodeTable *d_tab,
+static int launch_decode_exact(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
+                               unsigned long long range_end_bit, const DecodeTable *d_tab,
                                uint16_t *out16, DecWork *work, unsigned long long nch, unsigned long long c0,
                                unsigned long long c1)
 {
-    int rc = launch_sync2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false);
+    int rc = launch_sync2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, false, false);
     if (rc) return rc;
-    rc = launch_fix2(c, frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, c0, c1, false);
+    rc = launch_fix2(c, frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, false);
     if (rc) return rc;
     rc = launch_scan(c, work, nch, c0, c1);
     if (rc) return rc;
-    return launch_write2(c, frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out16, false);
+    return launch_write2(c, frame, frame_bytes, d_tab, work, nch, c0, c1, out16, false);
 }
 
 // A decode of one stream, all at once (launch_decode) or in slices of chunks as its bytes arrive from the host
@@ -497,21 +530,49 @@ int decode_begin(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64_
     job->n_symbols = n_symbols;
     job->tab = d_tab;
     job->out16 = reinterpret_cast<uint16_t *>(d_out);
-    const size_t off = 8u << 20;                        // behind the table-source / codebook workspace
+    const size_t off = WS_STAGE_OFFSET;
     int rc = ensure_ws(c, off + DecLayout::bytes(job->nch));
     if (rc) return rc;
     job->work = (uint8_t *)c->ws + off;
     job->total = reinterpret_cast<unsigned long long *>(job->work) + 2;     // DecWork::result[2]
     HF_CUDA(c, cudaMemsetAsync(job->work, 0, sizeof(DecWork), c->stream));
-    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, n_symbols, job->out16);
+    dec_start_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<DecWork *>(job->work), job->F0, n_symbols);
+    HF_LAUNCH_CHECK(c);
+    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, reinterpret_cast<DecWork *>(job->work), job->out16);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
 int decode_slice(Ctx *c, const DecodeJob &job, unsigned long long c0, unsigned long long c1)
 {
-    return launch_decode_exact(c, job.frame, job.frame_bytes, job.F0, job.frame_bytes * 8, job.n_symbols, job.tab, job.out16,
+    return launch_decode_exact(c, job.frame, job.frame_bytes, job.frame_bytes * 8, job.tab, job.out16,
                                reinterpret_cast<DecWork *>(job.work), job.nch, c0, c1);
+}
+
+// hf_decompress: the whole image, its header parsed on the device (d_info): the frame is the image itself, the first
+// code word sits wherever the header ends, and the output capacity is checked on the device.  Nothing here waits for
+// the host; the caller reads d_info and the flags after its one synchronisation.
+int launch_decompress_image(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, const hf_header_info_t *d_info,
+                            const DecodeTable *d_tab, uint8_t *d_out, uint64_t capacity)
+{
+    if ((uintptr_t)d_out & 1) return set_err(c, HF_ERR_ARG, "hf_decompress: output must be 2-byte aligned");
+    const uint8_t *frame = reinterpret_cast<const uint8_t *>((uintptr_t)d_file & ~(uintptr_t)15);
+    const unsigned long long lead = (uintptr_t)d_file & 15;
+    const unsigned long long frame_bytes = lead + file_bytes;
+    unsigned long long nch = (frame_bytes * 8 + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (nch == 0) nch = 1;
+    if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decompress: image too large");
+    const size_t off = WS_STAGE_OFFSET;
+    int rc = ensure_ws(c, off + DecLayout::bytes(nch));
+    if (rc) return rc;
+    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
+    HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
+    dec_start_info_kernel<<<1, 1, 0, c->stream>>>(work, d_info, d_tab, lead * 8, capacity, d_out);
+    HF_LAUNCH_CHECK(c);
+    uint16_t *out16 = reinterpret_cast<uint16_t *>(d_out);
+    HF_PROF(c, "dec_fill_kernel"); dec_fill_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_tab, work, out16);
+    HF_LAUNCH_CHECK(c);
+    return launch_decode_exact(c, frame, frame_bytes, frame_bytes * 8, d_tab, out16, work, nch, 0, nch);
 }
 
 // Decode with the records of a side index (n_subs u16, as the compressor's enc_index_kernel wrote them for this
@@ -532,9 +593,9 @@ int launch_decode_indexed(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes
     if (rc) return rc;
     rc = launch_scan(c, work, job.nch, 0, job.nch);
     if (rc) return rc;
-    rc = launch_idx_total(c, work, n_symbols);
+    rc = launch_idx_total(c, work);
     if (rc) return rc;
-    return launch_write2(c, job.frame, job.frame_bytes, job.F0, d_tab, work, job.nch, 0, job.nch, n_symbols, job.out16, true);
+    return launch_write2(c, job.frame, job.frame_bytes, d_tab, work, job.nch, 0, job.nch, job.out16, true);
 }
 
 // number of index records of a stream of stream_bytes bytes whose first code word sits start_bit bits after d_stream
@@ -559,13 +620,12 @@ int launch_decode(Ctx *c, const uint8_t *d_stream, uint64_t stream_bytes, uint64
 }
 
 // result[4] of a range call from the exact kernels' work area: -, overflow, symbols, flags
-__global__ void dec_result_kernel(const DecWork *__restrict__ work, unsigned long long out_symbols,
-                                  unsigned long long *__restrict__ result)
+__global__ void dec_result_kernel(const DecWork *__restrict__ work, unsigned long long *__restrict__ result)
 {
     result[0] = 0;
     result[1] = work->result[1];
     result[2] = work->result[2];
-    result[3] = (work->flags[1] ? 4ull : 0ull) | (work->result[2] > out_symbols ? 8ull : 0ull);
+    result[3] = (work->flags[1] ? 4ull : 0ull) | (work->result[2] > work->start[1] ? 8ull : 0ull);
 }
 
 // one rank's byte range of a sharded stream.  tail_only: just the overflow of the
@@ -586,26 +646,98 @@ int launch_decode_range(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, ui
     unsigned long long nch = (end_bit + CHUNK_BITS - 1) / CHUNK_BITS;
     if (nch == 0) nch = 1;
     if (nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_decode_range: range too large");
-    const size_t off = 8u << 20;
+    const size_t off = WS_STAGE_OFFSET;
     int rc = ensure_ws(c, off + DecLayout::bytes(nch));
     if (rc) return rc;
     DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + off);
     HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
+    dec_start_kernel<<<1, 1, 0, c->stream>>>(work, F0, tail_only ? ~0ull >> 8 : out_symbols);
+    HF_LAUNCH_CHECK(c);
     if (tail_only) {
-        rc = launch_sync2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, 0, nch, true);
+        rc = launch_sync2(c, frame, frame_bytes, end_bit, d_tab, work, nch, 0, nch, true, true);
         if (rc) return rc;
-        {
-            // the groups of the tail converge one by one on guessed starts; the repair carries the chain from the
-            // first of them (the lead-in, 240 KiB or more when the range is that long) to the range end
-            rc = launch_fix2(c, frame, frame_bytes, F0, end_bit, d_tab, work, nch, tail_first_chunk(nch) + GROUP_CHUNKS, nch, true);
-            if (rc) return rc;
-        }
+        // the groups of the tail converge one by one on guessed starts; the repair carries the chain from the
+        // first of them (the lead-in, 240 KiB or more when the range is that long) to the range end
+        rc = launch_fix2(c, frame, frame_bytes, end_bit, d_tab, work, nch, tail_first_chunk(nch) + GROUP_CHUNKS, nch, true);
+        if (rc) return rc;
     } else {
-        rc = launch_decode_exact(c, frame, frame_bytes, F0, end_bit, out_symbols, d_tab, reinterpret_cast<uint16_t *>(d_out),
-                                 work, nch, 0, nch);
+        rc = launch_decode_exact(c, frame, frame_bytes, end_bit, d_tab, reinterpret_cast<uint16_t *>(d_out), work, nch, 0, nch);
         if (rc) return rc;
     }
-    HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, tail_only ? ~0ull >> 8 : out_symbols, d_result);
+    HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, d_result);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+// ---- a rank's byte range in two phases around the hand-over collective (sharded.cu) ------------------------------
+// Phase A needs nothing from the other ranks: the whole range is synchronised SPECULATIVELY (every span from a guess,
+// the chunk chain repaired on the assumption that the stream re-synchronises), which already yields what the next
+// rank waits for, the overflow of the range's last code word past its end (d_probe[0]; d_probe[1] = the range's bits).
+// Phase B runs once the predecessor's overflow is known ON THE DEVICE (*d_first_bit, bits from the range's first byte):
+// the head of the range is repaired from that bit, the chunk counts are scanned and the symbols written.  Round 1 ran a
+// separate speculative pass over the range's tail for the hand-over and then the exact pass; here the one pass serves both.
+struct RangeGeom {
+    const uint8_t *frame;
+    unsigned long long lead, frame_bytes, end_bit, nch;
+};
+static int range_geom(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, RangeGeom *g)
+{
+    g->frame = reinterpret_cast<const uint8_t *>((uintptr_t)d_range & ~(uintptr_t)15);
+    g->lead = (unsigned long long)((uintptr_t)d_range & 15);
+    g->frame_bytes = g->lead + range_bytes + halo_bytes;
+    g->end_bit = (g->lead + range_bytes) * 8;
+    g->nch = (g->end_bit + CHUNK_BITS - 1) / CHUNK_BITS;
+    if (g->nch == 0) g->nch = 1;
+    if (g->nch > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "sharded decode: range too large");
+    return ensure_ws(c, WS_STAGE_OFFSET + DecLayout::bytes(g->nch));
+}
+
+__global__ void range_probe_kernel(const DecWork *__restrict__ work, unsigned long long range_bits,
+                                   unsigned long long *__restrict__ probe)
+{
+    probe[0] = work->result[1];
+    probe[1] = range_bits;
+}
+
+int launch_range_sync(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes, const DecodeTable *d_tab,
+                      unsigned long long *d_probe)
+{
+    RangeGeom g;
+    int rc = range_geom(c, d_range, range_bytes, halo_bytes, &g);
+    if (rc) return rc;
+    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + WS_STAGE_OFFSET);
+    HF_CUDA(c, cudaMemsetAsync(work, 0, sizeof(DecWork), c->stream));
+    if (range_bytes) {
+        rc = launch_sync2(c, g.frame, g.frame_bytes, g.end_bit, d_tab, work, g.nch, 0, g.nch, false, true);
+        if (rc) return rc;
+        rc = launch_fix2(c, g.frame, g.frame_bytes, g.end_bit, d_tab, work, g.nch, 0, g.nch, true);
+        if (rc) return rc;
+    }
+    range_probe_kernel<<<1, 1, 0, c->stream>>>(work, range_bytes * 8ull, d_probe);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
+int launch_range_write(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
+                       const unsigned long long *d_first_bit, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
+                       unsigned long long *d_result)
+{
+    if ((uintptr_t)d_out & 1) return set_err(c, HF_ERR_ARG, "sharded decode: output must be 2-byte aligned");
+    RangeGeom g;
+    int rc = range_geom(c, d_range, range_bytes, halo_bytes, &g);       // the same geometry (and workspace) as phase A
+    if (rc) return rc;
+    DecWork *work = reinterpret_cast<DecWork *>((uint8_t *)c->ws + WS_STAGE_OFFSET);
+    dec_start_range_kernel<<<1, 1, 0, c->stream>>>(work, d_first_bit, g.lead * 8, out_symbols);
+    HF_LAUNCH_CHECK(c);
+    if (range_bytes) {
+        rc = launch_fix_head(c, g.frame, g.frame_bytes, g.end_bit, d_tab, work, g.nch);
+        if (rc) return rc;
+        rc = launch_scan(c, work, g.nch, 0, g.nch);
+        if (rc) return rc;
+        rc = launch_write2(c, g.frame, g.frame_bytes, d_tab, work, g.nch, 0, g.nch, reinterpret_cast<uint16_t *>(d_out), false);
+        if (rc) return rc;
+    }
+    HF_PROF(c, "dec_result_kernel"); dec_result_kernel<<<1, 1, 0, c->stream>>>(work, d_result);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

@@ -408,9 +408,10 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
     if (live) end = pos - lim;          // ran to the limit (pos >= lim)
 }
 
-// One warp converges on chunk c.  exact: the chunk's first code word starts `start` bits into it (the stream head,
-// or the true overflow of the chunk before when a chunk is redone); otherwise lane 0 starts from a guess like every
-// other lane and dec_fix2_kernel repairs the chunk's first subsequences afterwards.  dense: code words this warp
+// One warp converges on chunk c.  xstart: frame bit at which a code word is KNOWN to start (the stream head, or the
+// true overflow of the chunk before when a chunk is redone), NO_START when there is none.  Spans that end before it
+// hold no code word; the lane whose span holds it starts there; every other lane 0 starts from a guess like the lanes
+// behind it, and dec_fix2_kernel repairs the chunk's first subsequences afterwards.  dense: code words this warp
 // counted in its last chunk (see DENSE4_MIN).  mark: reset the chunk's repair mark (the regroup kernel must not).
 // Short code words come several to a 14-bit look-up; when the warp's last chunk held more than DENSE4_MIN of them (under
 // ~10 bits each) the walks take all the code words an entry holds in one step (MULTI), which costs every step a few
@@ -418,14 +419,17 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
 constexpr uint32_t DENSE4_MIN = CHUNK_BITS / 10u;
 template <bool MULTI>
 __device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, uint32_t rec_a, unsigned long long c,
-                                           bool exact, uint32_t start, bool mark, uint32_t &bad, uint32_t &dense)
+                                           unsigned long long xstart, bool mark, uint32_t &bad, uint32_t &dense)
 {
     const uint32_t lane = threadIdx.x & 31;
     DecLayout L(S.work, S.nch);
     const unsigned long long X = c * CHUNK_BITS + (unsigned long long)lane * LANE_BITS;
-    const uint32_t lim = lane_limit(X, S.range_end_bit);
-    const bool fixed = lane == 0;                       // lane 0 has no predecessor in the warp: exact start or guess
-    uint32_t p = (exact && lane == 0) ? start : (X >= S.F0 ? spec_start(X, S.F0, S.g) : 0u);
+    const bool have_x = xstart != NO_START;
+    const bool before = have_x && X + LANE_BITS <= xstart;          // my span ends before the first code word
+    const bool holds = have_x && xstart >= X && xstart < X + LANE_BITS;
+    const uint32_t lim = before ? 0u : lane_limit(X, S.range_end_bit);
+    const bool fixed = lane == 0 || holds;              // no predecessor in the warp (guess), or the known start
+    uint32_t p = holds ? (uint32_t)(xstart - X) : (X >= S.F0 ? spec_start(X, S.F0, S.g) : 0u);
     // `end`: overflow of the walk from p.  The record row describes the walk from rec_p, which ended at rec_end.
     // memo: up to four (start + 1, end) pairs of walks of this span.  Data that does not re-synchronise (a long run
     // of one code word is periodic) makes the fix-point hand a lane the same few starts again and again; a remembered
@@ -514,7 +518,7 @@ __device__ __forceinline__ void sync4_setup(uint32_t *smem, const DecodeTable *t
 }
 
 __global__ void __launch_bounds__(S4_THREADS, 1)
-dec_sync4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+dec_sync4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                  unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
                  unsigned long long nch, unsigned long long c_first, unsigned long long c_last, uint32_t speculative)
 {
@@ -522,15 +526,18 @@ dec_sync4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
     if (tab->single_sym) return;                        // empty payload, see dec_fill_kernel
     uint32_t d14_a, row_a, rec_a;
     sync4_setup(s4_smem, tab, d14_a, row_a, rec_a);
+    // speculative: the start of the range is not known (yet): every span starts from a guess, code word boundaries
+    // are not assumed to lie on a lattice
+    const unsigned long long F0 = speculative ? 0ull : work->start[0];
     const Sync4Ctx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, d14_a, speculative ? 1u : tab->len_gcd, 32u - tab->k2};
     __syncthreads();                                    // plane loaded; the warps are on their own from here
     const uint32_t wid = threadIdx.x >> 5;
     uint32_t bad = 0, dense = 0;
     for (unsigned long long c = c_first + (unsigned long long)blockIdx.x * S4_WARPS + wid; c < c_last;
          c += (unsigned long long)gridDim.x * S4_WARPS) {
-        const bool exact = c == 0 && !speculative;
-        if (dense > DENSE4_MIN) sync_chunk<true>(S, row_a, rec_a, c, exact, (uint32_t)F0, true, bad, dense);
-        else sync_chunk<false>(S, row_a, rec_a, c, exact, (uint32_t)F0, true, bad, dense);
+        const unsigned long long xs = speculative ? NO_START : F0;
+        if (dense > DENSE4_MIN) sync_chunk<true>(S, row_a, rec_a, c, xs, true, bad, dense);
+        else sync_chunk<false>(S, row_a, rec_a, c, xs, true, bad, dense);
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
@@ -543,7 +550,7 @@ dec_sync4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_byt
 // recorded — up to, not into, the next run's head.  All decisions are taken by lane 0 and broadcast.  What this leaves
 // open (a chain that reaches another run) is found by dec_verify_kernel and settled by the serial kernel.
 __global__ void __launch_bounds__(S4_THREADS, 1)
-dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                     unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
                     unsigned long long nch, unsigned long long c_first, unsigned long long c_last, uint32_t speculative)
 {
@@ -552,6 +559,7 @@ dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_
     if (tab->single_sym) return;
     uint32_t d14_a, row_a, rec_a;
     sync4_setup(s4_smem, tab, d14_a, row_a, rec_a);
+    const unsigned long long F0 = speculative ? 0ull : work->start[0];
     const Sync4Ctx S{frame, frame_bytes, F0, range_end_bit, nch, tab, work, d14_a, speculative ? 1u : tab->len_gcd, 32u - tab->k2};
     __syncthreads();
     DecLayout L(work, nch);
@@ -570,7 +578,7 @@ dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_
         s = __shfl_sync(0xFFFFFFFFu, s, 0);
         bool in_run = true;
         for (unsigned long long cur = c;;) {
-            sync_chunk<false>(S, row_a, rec_a, cur, true, s, false, bad, dense);
+            sync_chunk<false>(S, row_a, rec_a, cur, cur * CHUNK_BITS + s, false, bad, dense);
             const unsigned long long next = cur + 1;
             if (next >= c_last) break;
             uint32_t dirty = 0, first = 0, e = 0;
@@ -596,12 +604,18 @@ dec_regroup4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
+// the chunk that holds the first code word: boundaries up to and including its own have nothing to repair
+__device__ __forceinline__ unsigned long long first_chunk(const DecWork *work, uint32_t speculative)
+{
+    return speculative ? 0ull : work->start[0] / CHUNK_BITS;
+}
+
 // every group must start where the group before it ends; what the parallel repairs left open goes to the serial kernel
 __global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                                  unsigned long long g_first, unsigned long long g_last)
+                                  unsigned long long g_first, unsigned long long g_last, uint32_t speculative)
 {
     const unsigned long long g = (g_first ? g_first : 1) + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= g_last || tab->single_sym) return;
+    if (g >= g_last || tab->single_sym || g <= first_chunk(work, speculative)) return;
     DecLayout L(work, nch);
     const unsigned long long c = g * GROUP_CHUNKS;
     if (c >= nch) return;
@@ -615,9 +629,9 @@ __global__ void dec_verify_kernel(const DecodeTable *__restrict__ tab, DecWork *
 // it derives itself from the chunk's records (no CTA-wide scan, no CTA barrier after the planes are loaded).
 // The symbols of a unit are compacted in the warp's staging window and leave with aligned 128-bit stores.
 __global__ void __launch_bounds__(W3_THREADS, 1)
-dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long F0,
+dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
-                  unsigned long long c0, unsigned long long c1, unsigned long long n_symbols,
+                  unsigned long long c0, unsigned long long c1,
                   uint16_t *__restrict__ out, uint32_t check, uint32_t upw)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
@@ -625,6 +639,8 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     uint32_t *s_t14 = w3_smem;                                                  // 2^MICRO_K
     uint16_t *s_leaves = reinterpret_cast<uint16_t *>(s_t14 + (1u << MICRO_K)); // NSYM
     if (tab->single_sym) return;
+    const unsigned long long F0 = work->start[0], n_symbols = work->start[1];
+    const unsigned long long head_sub = F0 / SUB_BITS;         // the subsequence that holds the first code word
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint16_t *sout = s_leaves + NSYM + wid * (WIN + 8);                         // this warp's window
@@ -650,7 +666,7 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
         const unsigned long long c = ug0 / UPC;
         const uint32_t u0 = (uint32_t)(ug0 % UPC);
         const unsigned long long cbase = L.chunkBase[c];
-        if (cbase >= n_symbols) continue;
+        if (cbase >= n_symbols || (c + 1) * DEC_THREADS <= head_sub) continue;     // nothing left to write / before the first code word
         uint32_t ninf = L.info[c * DEC_THREADS + 32 * u0 + lane];
         uint32_t nr[9];
         load_sub_raw(nr, frame, frame_bytes, c, 32 * u0 + lane, lane);
@@ -678,7 +694,7 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             load_sub_raw(nr, frame, frame_bytes, c, t + 32, lane);
         }
         const uint32_t cnt = inf >> 6;
-        uint32_t pos = (c == 0 && t == 0) ? (uint32_t)F0 : (inf & 63u);     // the stream head may sit past bit 63
+        uint32_t pos = (c * DEC_THREADS + t == head_sub) ? (uint32_t)(F0 % SUB_BITS) : (inf & 63u);   // the head may sit past bit 63
         uint32_t x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
@@ -801,14 +817,14 @@ __global__ void idx_chunks_kernel(DecWork *work, unsigned long long nch)
 }
 
 // the records of a side index must account for every symbol of the stream, no more, no fewer
-__global__ void idx_total_kernel(DecWork *work, unsigned long long n_symbols)
+__global__ void idx_total_kernel(DecWork *work)
 {
-    if (work->result[2] != n_symbols) atomicExch(&work->flags[1], 1ull);
+    if (work->result[2] != work->start[1]) atomicExch(&work->flags[1], 1ull);
 }
 
-int launch_idx_total(Ctx *c, DecWork *work, unsigned long long n_symbols)
+int launch_idx_total(Ctx *c, DecWork *work)
 {
-    HF_PROF(c, "idx_total_kernel"); idx_total_kernel<<<1, 1, 0, c->stream>>>(work, n_symbols);
+    HF_PROF(c, "idx_total_kernel"); idx_total_kernel<<<1, 1, 0, c->stream>>>(work);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -881,13 +897,13 @@ __device__ __forceinline__ void sub_count(const DecodeTable *tab, const uint8_t 
 // Returns true when that happened before the chunk ended; otherwise chunkE[c] is the chunk's new overflow.
 __device__ bool fix_chunk2(const DecodeTable *tab, const uint8_t *frame, unsigned long long frame_bytes,
                            unsigned long long range_end_bit, DecWork *work, DecLayout &L, unsigned long long c, uint32_t s,
-                           uint32_t &bad)
+                           uint32_t &bad, uint32_t t0 = 0)
 {
     uint16_t *info = L.info + c * DEC_THREADS;
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t q = s;
     long long delta = 0;
-    for (uint32_t t = 0; t < DEC_THREADS; t++) {
+    for (uint32_t t = t0; t < DEC_THREADS; t++) {
         const uint32_t lim = sub_limit(c, t, range_end_bit);
         if (lim == 0) break;
         uint32_t end, cnt;
@@ -936,10 +952,11 @@ __device__ bool probe_chunk(const DecodeTable *tab, const uint8_t *frame, unsign
 // subsequences is left to dec_regroup_kernel.
 __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                 unsigned long long range_end_bit, const DecodeTable *__restrict__ tab, DecWork *work,
-                                unsigned long long nch, unsigned long long g_first, unsigned long long g_last)
+                                unsigned long long nch, unsigned long long g_first, unsigned long long g_last,
+                                uint32_t speculative)
 {
     const unsigned long long g = (g_first ? g_first : 1) + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= g_last || tab->single_sym) return;
+    if (g >= g_last || tab->single_sym || g <= first_chunk(work, speculative)) return;
     const unsigned long long c = g * GROUP_CHUNKS;
     if (c >= nch) return;
     DecLayout L(work, nch);
@@ -960,12 +977,13 @@ __global__ void dec_fix2_kernel(const uint8_t *__restrict__ frame, unsigned long
 __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                                        unsigned long long range_end_bit, const DecodeTable *__restrict__ tab,
                                        DecWork *work, unsigned long long nch, unsigned long long c0,
-                                       unsigned long long c1)
+                                       unsigned long long c1, uint32_t speculative)
 {
     if (work->flags[0] == 0 || tab->single_sym) return;
     DecLayout L(work, nch);
     uint32_t bad = 0;
-    for (unsigned long long c = c0 ? c0 : 1; c < c1; c++) {
+    const unsigned long long cf = first_chunk(work, speculative);
+    for (unsigned long long c = max(c0 ? c0 : 1ull, cf + 1); c < c1; c++) {
         const uint32_t s = L.chunkE[c - 1];
         if (s == (uint32_t)(L.info[c * DEC_THREADS] & 63u)) continue;
         fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, s, bad);
@@ -974,8 +992,51 @@ __global__ void dec_fix2_serial_kernel(const uint8_t *__restrict__ frame, unsign
     work->flags[0] = 0;                                 // settled (the next slice starts clean)
 }
 
+
+// A range whose chunks were synchronised speculatively (every span from a guess, dec_fix2 between the chunks) learns
+// where its first code word starts (work->start[0], e.g. the predecessor rank's overflow, which arrives by a
+// collective): the chunks before it count nothing, the subsequences before it in its chunk neither, and one thread
+// walks from it until it lands on a start the synchronisation recorded — after a subsequence or two on data that
+// re-synchronises; a chain that does not is carried on chunk by chunk, and the overflow past the range end follows it.
+__global__ void __launch_bounds__(256)
+dec_fix_head_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
+                    const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch)
+{
+    if (tab->single_sym) return;
+    DecLayout L(work, nch);
+    const unsigned long long F0 = work->start[0];
+    const bool none = F0 >= range_end_bit;              // no code word starts in this range: it only passes the bit on
+    const unsigned long long cf = none ? nch : F0 / CHUNK_BITS;
+    for (unsigned long long c = threadIdx.x; c < cf; c += blockDim.x) L.chunkCnt[c] = 0;
+    if (none) {
+        if (threadIdx.x == 0) { work->result[1] = F0 - range_end_bit; work->start[1] = 0; }
+        return;
+    }
+    if (threadIdx.x != 0) return;
+    const uint32_t t0 = (uint32_t)((F0 % CHUNK_BITS) / SUB_BITS);
+    uint16_t *info = L.info + cf * DEC_THREADS;
+    uint32_t gone = 0;
+    for (uint32_t t = 0; t < t0; t++) { gone += info[t] >> 6; info[t] = 0; }
+    L.chunkCnt[cf] -= gone;
+    uint32_t bad = 0;
+    if ((uint32_t)(info[t0] & 63u) != (uint32_t)(F0 % SUB_BITS) || (info[t0] >> 6) == 0 || F0 % SUB_BITS >= 64) {
+        bool met = fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, cf, (uint32_t)(F0 % SUB_BITS), bad, t0);
+        for (unsigned long long c = cf + 1; !met && c < nch; c++)
+            met = fix_chunk2(tab, frame, frame_bytes, range_end_bit, work, L, c, L.chunkE[c - 1], bad);
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+int launch_fix_head(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long range_end_bit,
+                    const DecodeTable *d_tab, DecWork *work, unsigned long long nch)
+{
+    HF_PROF(c, "dec_fix_head_kernel"); dec_fix_head_kernel<<<1, 256, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch);
+    HF_LAUNCH_CHECK(c);
+    return HF_OK;
+}
+
 // chunks [c0, c1) (a slice of the stream, or all of it); everything before c0 is final
-int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                 unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
                 unsigned long long c0, unsigned long long c1, bool speculative)
 {
@@ -984,16 +1045,16 @@ int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, un
     if (g_last <= (g_first ? g_first : 1)) return HF_OK;
     const unsigned long long ng = g_last - (g_first ? g_first : 1);
     HF_CUDA(c, cudaMemsetAsync(&work->flags[3], 0, 8, c->stream));
-    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, g_first, g_last);
+    HF_PROF(c, "dec_fix2_kernel"); dec_fix2_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     unsigned long long grid = (ng + S4_WARPS - 1) / S4_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_regroup4_kernel");
-    dec_regroup4_kernel<<<(unsigned)grid, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
+    dec_regroup4_kernel<<<(unsigned)grid, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_verify_kernel"); dec_verify_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, c->stream>>>(d_tab, work, nch, g_first, g_last);
+    HF_PROF(c, "dec_verify_kernel"); dec_verify_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, c->stream>>>(d_tab, work, nch, g_first, g_last, speculative ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
-    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1);
+    HF_PROF(c, "dec_fix2_serial_kernel"); dec_fix2_serial_kernel<<<1, 1, 0, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch, c0, c1, speculative ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -1001,9 +1062,9 @@ int launch_fix2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, un
 // -------------------------------------------------------------------------------------------------
 // -------------------------------------------------------------------------------------------------
 // chunks [c0, c1), c0 a multiple of GROUP_CHUNKS; tail_only ignores the range
-int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                  unsigned long long range_end_bit, const DecodeTable *d_tab, DecWork *work, unsigned long long nch,
-                 unsigned long long c0, unsigned long long c1, bool tail_only)
+                 unsigned long long c0, unsigned long long c1, bool tail_only, bool speculative)
 {
     if (!c->smem_attr[ATTR_SYNC]) {
         HF_CUDA(c, cudaFuncSetAttribute(dec_sync4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM));
@@ -1023,15 +1084,15 @@ int launch_sync2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, u
     unsigned long long grid4 = (ngroups - g_first + S4_WARPS - 1) / S4_WARPS;
     if (grid4 > (unsigned long long)c->sm_count) grid4 = c->sm_count;
     HF_PROF(c, "dec_sync4_kernel");
-    dec_sync4_kernel<<<(unsigned)grid4, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, F0, range_end_bit, d_tab, work, nch,
-                                                                        g_first, ngroups, tail_only ? 1u : 0u);
+    dec_sync4_kernel<<<(unsigned)grid4, S4_THREADS, S4_SMEM, c->stream>>>(frame, frame_bytes, range_end_bit, d_tab, work, nch,
+                                                                        g_first, ngroups, (tail_only || speculative) ? 1u : 0u);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
 
-int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, unsigned long long F0,
+int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
                   const DecodeTable *d_tab, DecWork *work, unsigned long long nch, unsigned long long c0,
-                  unsigned long long c1, unsigned long long n_symbols, uint16_t *out, bool check)
+                  unsigned long long c1, uint16_t *out, bool check)
 {
     if (c1 <= c0) return HF_OK;
     if (!c->smem_attr[ATTR_WRITE]) {
@@ -1046,7 +1107,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes, 
     unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, F0, d_tab, work, nch, c0, c1, n_symbols, out, check ? 1u : 0u, upw);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, d_tab, work, nch, c0, c1, out, check ? 1u : 0u, upw);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

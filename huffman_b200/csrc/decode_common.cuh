@@ -49,10 +49,16 @@ __host__ __device__ inline unsigned long long tail_first_chunk(unsigned long lon
 }
 
 
+// NO_START: no exact start is known (a speculative pass: every span starts from a guess)
+constexpr unsigned long long NO_START = ~0ull;
 struct DecWork {
     unsigned long long result[4];       // [1] overflow of the last code word past the range end, [2] symbols in the range
     unsigned long long flags[4];        // [0] a group does not start where the one before ends (serial kernel needed),
-                                        // [1] invalid code met, [2] table error, [3] a group was left to dec_regroup_kernel
+                                        // [1] invalid code met, [2] output capacity too small, [3] a group was left to dec_regroup4_kernel
+    // where the decode starts and how much it may write, DEVICE resident so that a header parsed on the device or a
+    // hand-over bit that arrives by a collective never has to visit the host: [0] frame bit of the first code word
+    // (F0; chunks and lanes before it hold no code word), [1] symbols to write at most, [2] spare, [3] spare
+    unsigned long long start[4];
     // followed by: chunkBase[nch] u64, chunkCnt[nch] u32, chunkE[nch] u32 (overflow past the chunk's end),
     //              chunkE2[nch] u32 (0xFFFFFFFF, or CHUNK_DIRTY on the first chunk of a group that must be redone),
     //              info[nch * DEC_THREADS] u16

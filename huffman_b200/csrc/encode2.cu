@@ -79,9 +79,10 @@ __device__ __forceinline__ void load_unit(const uint8_t *in_bytes, uint64_t n_sy
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BITS_THREADS)
 enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, Enc2Work W,
-                uint64_t ngroups)
+                uint64_t ngroups, const ShardPlan *__restrict__ plan)
 {
     extern __shared__ __align__(16) uint8_t s_len[];           // lenf plane, 64 KiB
+    if (plan && plan->status) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(cb->lenf);
@@ -379,9 +380,14 @@ __device__ __noinline__ void encode_unit_general(const UnitCtx &C, uint64_t unit
 
 __global__ void __launch_bounds__(E2_THREADS, 1)
 encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codebook *__restrict__ cb, uint8_t *stream,
-               uint64_t start_bit, Enc2Work W, uint64_t ngroups)
+               uint64_t start_bit, Enc2Work W, uint64_t ngroups, const ShardPlan *__restrict__ plan)
 {
     extern __shared__ __align__(16) uint8_t e2_smem[];
+    if (plan) {                                         // the start bit is the device's: sizes never visit the host
+        if (plan->status) return;
+        stream += plan->local_start_bit >> 3;
+        start_bit = plan->local_start_bit & 7;
+    }
     const uint16_t *p16 = reinterpret_cast<const uint16_t *>(e2_smem);
     const uint8_t *p8 = e2_smem + NSYM * 2;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -693,7 +699,7 @@ static int enc2_work(Ctx *c, uint64_t n_sym, Enc2Work *W, uint64_t *ngroups_out,
     const uint64_t ngroups = (n_sym + GROUP_SYMS - 1) / GROUP_SYMS;
     const uint64_t nblocks = (ngroups + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK;
     if (nblocks > 0x7FFFFFFFull) return set_err(c, HF_ERR_ARG, "hf_encode: input too large");
-    const size_t off = 8u << 20;
+    const size_t off = WS_STAGE_OFFSET;
     const size_t b_units = ((size_t)ngroups * GROUP_UNITS * 4 + 255) & ~(size_t)255;
     const size_t b_gbits = ((size_t)ngroups * 4 + 255) & ~(size_t)255;
     const size_t b_gstart = ((size_t)ngroups * 8 + 255) & ~(size_t)255;
@@ -738,9 +744,8 @@ int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Cod
 }
 
 int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook *d_cb, uint8_t *d_stream,
-                  uint64_t start_bit, uint32_t maxlen_hint)
+                  uint64_t start_bit, const ShardPlan *plan)
 {
-    (void)maxlen_hint;
     const uint64_t n_sym = n_bytes / 2;
     if (n_sym == 0) return HF_OK;
     if ((uintptr_t)d_in & 1) return set_err(c, HF_ERR_ARG, "hf_encode: input must be 2-byte aligned");
@@ -761,7 +766,7 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     const uint64_t bw = BITS_THREADS / 32;
     uint64_t bgrid = (ngroups + bw - 1) / bw;
     if (bgrid > (uint64_t)(3 * c->sm_count)) bgrid = 3 * c->sm_count;
-    HF_PROF(c, "enc_bits_kernel"); enc_bits_kernel<<<(unsigned)bgrid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups);
+    HF_PROF(c, "enc_bits_kernel"); enc_bits_kernel<<<(unsigned)bgrid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, plan);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "enc_scan1_kernel"); enc_scan1_kernel<<<(unsigned)nblocks, 1024, 0, c->stream>>>(W, ngroups);
     HF_LAUNCH_CHECK(c);
@@ -769,7 +774,7 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     HF_LAUNCH_CHECK(c);
     uint64_t grid = (ngroups + E2_WARPS - 1) / E2_WARPS;
     if (grid > (uint64_t)c->sm_count) grid = c->sm_count;
-    HF_PROF(c, "encode2_kernel"); encode2_kernel<<<(unsigned)grid, E2_THREADS, E2_SMEM, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, W, ngroups);
+    HF_PROF(c, "encode2_kernel"); encode2_kernel<<<(unsigned)grid, E2_THREADS, E2_SMEM, c->stream>>>(d_in, n_sym, d_cb, d_stream, start_bit, W, ngroups, plan);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }

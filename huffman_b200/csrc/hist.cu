@@ -174,6 +174,7 @@ int launch_histogram(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, unsigned lon
         uint64_t per_cta = (uint64_t)HIST_THREADS * HIST_UNROLL;          // vectors per CTA strip
         int grid = (int)((n_vec + per_cta - 1) / per_cta);
         if (grid > c->sm_count) grid = c->sm_count;
+        if ((size_t)grid * HIST_WORDS * sizeof(uint32_t) > WS_SCRATCH_BYTES) grid = (int)(WS_SCRATCH_BYTES / (HIST_WORDS * sizeof(uint32_t)));
         size_t part_bytes = (size_t)grid * HIST_WORDS * sizeof(uint32_t);
         int rc = ensure_ws(c, part_bytes);
         if (rc) return rc;

@@ -21,9 +21,13 @@ Decompress (the format has no offset index: only rank 0 knows where its first co
   3. the counts give every rank's output offset.  A stream that fails the check (it does not
      self-synchronise) is gathered and decoded on rank 0 by the exact kernels.
 
-The kernels are reached through a `stages` object (huffman_b200.codec.Codec in production: CUDA
-only, no CPU fallback); the CPU gloo tests plug in an oracle-backed stand-in to exercise this
-host logic without a GPU.
+Two drivers of the same protocol:
+  * production: the C ABI (`hf_compress_sharded` / `hf_decompress_sharded`, csrc/sharded.cu) — stages AND collectives
+    (NCCL) on the context's stream, bit counts and hand-over bits read from device memory, one host synchronisation
+    per call.  Used whenever the stages object carries an NCCL communicator (`Codec.comm_init`).
+  * this file's Python loop over a `stages` object and torch.distributed collectives: the transport-agnostic
+    restatement (any backend; the CPU gloo tests plug in an oracle-backed stand-in for the kernels).  It keeps
+    round 1's shape — sizes visit the host between the stages — and is what the C path is checked against.
 """
 from dataclasses import dataclass
 
@@ -88,9 +92,11 @@ def seam_plan(starts, bits, image_bytes, rank):
 
 
 class ShardedCodec:
-    def __init__(self, stages, group=None, device=None):
+    def __init__(self, stages, group=None, device=None, use_c=None):
         self.st = stages
         self.group = group
+        # the C-ABI driver when the stages object has an NCCL communicator (or one rank: nothing to communicate)
+        self.use_c = bool(getattr(stages, "has_comm", False)) if use_c is None else use_c
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.device = device if device is not None else getattr(stages, "device", torch.device("cpu"))
@@ -124,6 +130,8 @@ class ShardedCodec:
         """chunk: this rank's bytes shard_bounds(n_total, world)[rank] (uint8 tensor on the device).
         Returns a Slice.  Synchronises with the host once (the bit counts)."""
         st = self.st
+        if self.use_c:
+            return self._compress_c(chunk, n_total, last_byte, out)
         hist = st.histogram(chunk)                                     # local counts
         if self.world > 1:
             total = hist.clone()
@@ -166,6 +174,24 @@ class ShardedCodec:
                 out[dst:dst + ln] |= recs[r, src:src + ln]
         return Slice(out, first_byte, range_bytes, start, end, image_bytes, n_total)
 
+    def _compress_c(self, chunk, n_total, last_byte, out):
+        st = self.st
+        need = st.compress_bound(chunk.numel()) + HALO + 64
+        for attempt in range(2):
+            if out is None or out.numel() < need or (out.data_ptr() & 15):
+                out = torch.empty(need, dtype=torch.uint8, device=chunk.device)
+            try:
+                info = st.compress_sharded(chunk, n_total, last_byte, out)
+                break
+            except Exception as e:                                     # HF_ERR_CAPACITY comes back on EVERY rank: all retry
+                if getattr(e, "code", 0) != 3 or attempt:
+                    raise
+                need = max(need, chunk.numel() * 4 + st.compress_bound(0) + (1 << 20))   # codes <= 64 bits: never more
+                out = None
+        self.collectives = st.collective_count()
+        return Slice(out, int(info.first_byte), int(info.range_bytes), int(info.start_bit), int(info.end_bit),
+                     int(info.image_bytes), n_total)
+
     def gather_image(self, sl):
         """the whole image on every rank (tests, the CLI)"""
         sizes = self._all_gather(torch.tensor([sl.first_byte, sl.range_bytes], dtype=torch.int64,
@@ -186,6 +212,8 @@ class ShardedCodec:
         the bit positions of the slices are NOT (the format has no offset index).
         Returns (this rank's decoded bytes, their byte offset in the original, n_total)."""
         st = self.st
+        if self.use_c:
+            return self._decompress_c(sl, out)
         if self.world > 1:
             # rank 0 parses the header; the others rebuild the table from the broadcast header bytes
             meta = torch.zeros(1, dtype=torch.int64, device=sl.buf.device)
@@ -251,6 +279,24 @@ class ShardedCodec:
             offs.append(offs[-1] + c)
         mine_n = max(0, min(counts[self.rank], n_sym_total - offs[self.rank]))
         return out[:2 * mine_n], 2 * min(offs[self.rank], n_sym_total), n_total
+
+    def _decompress_c(self, sl, out):
+        st = self.st
+        dev = sl.buf.device
+        cap = sl.n_total // self.world + (1 << 17) if out is None else out.numel()
+        for attempt in range(2):
+            if out is None or out.numel() < cap:
+                out = torch.empty(cap, dtype=torch.uint8, device=dev)
+            res = st.decompress_sharded(sl.buf, sl.range_bytes, HALO, sl.image_bytes, out)
+            self.collectives = st.collective_count()
+            if res.status != 2:
+                break
+            cap = 2 * int(res.needed_symbols) + 64         # the same verdict on every rank: all retry
+            out = None
+        n_total = int(res.n_total)
+        if res.status == 1:
+            return self._decompress_on_rank0(sl, n_total)
+        return out[:int(res.out_bytes)], int(res.out_offset), n_total
 
     def _decompress_on_rank0(self, sl, n_total):
         """streams that do not self-synchronise (SURVEY.md 7 "adversarial streams"): no rank can find its

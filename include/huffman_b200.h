@@ -91,10 +91,6 @@ typedef struct {
 int hf_profile_enable(hf_ctx *ctx, int on);
 int hf_profile_read(hf_ctx *ctx, hf_kernel_time_t *out, uint32_t cap, uint32_t *n_out);
 
-/* development aid (phase-timing builds): synchronises and copies a piece of the context's
- * device workspace to the host */
-int hf_debug_read_ws(hf_ctx *ctx, uint64_t off, void *h_dst, uint64_t bytes);
-
 /* pinned host buffers for the host-facing calls (C:343 uses cudaHostAlloc) */
 int hf_host_alloc(void **h_ptr, size_t bytes);
 int hf_host_free(void *h_ptr);
@@ -144,8 +140,9 @@ int hf_header_pack(hf_ctx *ctx, const void *d_codebook, uint64_t n_bytes, uint32
 int hf_encode(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, const void *d_codebook,
               uint8_t *d_stream, uint64_t start_bit);
 
-/* whole `archive` data path on device buffers: histogram, codebook, header, encode.
- * Synchronises once (to learn the size); *h_file_bytes receives the image size. */
+/* whole `archive` data path on device buffers: histogram, codebook, header, encode.  The sizes and the start bit of the
+ * payload stay on the device (the capacity is checked there): nothing waits for the host until everything is enqueued.
+ * Synchronises once, at the end; *h_file_bytes receives the image size (also when it exceeds the capacity). */
 int hf_compress(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, uint8_t *d_file,
                 uint64_t capacity, uint64_t *h_file_bytes);
 
@@ -183,11 +180,8 @@ int hf_decode_range(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes, u
                     uint64_t first_bit, const void *d_decode_table, uint8_t *d_out, uint64_t out_symbols,
                     uint64_t *d_result);
 
-/* Kept for ABI compatibility: the decoder has ONE mode, exact self-synchronising decode (an earlier revision also had a
- * speculative single-pass decoder that this switch turned off).  The argument is stored and ignored. */
-int hf_set_decode_mode(hf_ctx *ctx, int exact_only);
-
-/* whole `extract` data path on device buffers.  Synchronises. */
+/* whole `extract` data path on device buffers: the header is parsed and the tables are built on the device, the decode
+ * starts where the device says the header ends, the capacity is checked there.  Synchronises once, at the end. */
 int hf_decompress(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, uint8_t *d_out,
                   uint64_t capacity, uint64_t *h_out_bytes);
 
@@ -205,6 +199,100 @@ int hf_compress_indexed(hf_ctx *ctx, const uint8_t *d_in, uint64_t n_bytes, uint
                         uint64_t *h_file_bytes, uint8_t *d_index, uint64_t index_capacity, uint64_t *h_index_bytes);
 int hf_decompress_indexed(hf_ctx *ctx, const uint8_t *d_file, uint64_t file_bytes, const uint8_t *d_index,
                           uint64_t index_bytes, uint8_t *d_out, uint64_t capacity, uint64_t *h_out_bytes);
+
+/* ---- sharded job: ONE stream over several GPUs ------------ */
+
+/* The reference is single-GPU (h:678 queries device 0; no cudaSetDevice, no NCCL anywhere): this layer is new, the
+ * format is not — the slices of the ranks, laid end to end in rank order, are the byte-identical file.  One process
+ * (or host thread) and one context per GPU.  The input is cut at multiples of 16 bytes (hf_shard_bounds); every rank
+ * histograms its chunk, the histogram is all-reduced, every rank builds the identical codebook (C:378-425, h:353-494),
+ * an all-gather of one u64 (the shard's payload bits) gives every rank its global start bit ON THE DEVICE, and the
+ * rank packs its slice of the single stream at that bit phase (C:541-588); seam bytes are OR-merged from an all-gather
+ * of 48 bytes.  Decompression (new: D:259-284 decodes serially on the host): the header is broadcast, every rank
+ * synchronises its byte range speculatively, an all-gather of the overflows hands every rank its first bit on the
+ * device, and an all-gather of the counts its output offset.  A step has three collectives each way plus the header
+ * broadcast, all on the context's stream (NCCL, loaded at run time), and ONE host synchronisation, at its end. */
+#define HF_SHARD_HALO 32u         /* bytes of the following slice kept behind each slice (read-ahead of the decoder) */
+#define HF_SHARD_REC_BYTES 48u    /* seam record of a rank: its first 32 bytes, its last byte, padding */
+#define HF_SHARD_MAX_RANKS 64u
+#define HF_HEADER_MAX 720928u     /* >= any header: 4 + 65536 * (16 + 8 + 64) / 8 + 8, rounded up to 16 */
+
+typedef struct { char internal[128]; } hf_unique_id_t;      /* an ncclUniqueId */
+
+typedef struct {
+    uint64_t first_byte;          /* index of slice[0] in the whole image */
+    uint64_t range_bytes;         /* bytes this rank owns: the ranges of consecutive ranks tile the image */
+    uint64_t start_bit, end_bit;  /* global bits of this rank's payload */
+    uint64_t image_bytes;         /* size of the whole image */
+    uint64_t n_total;             /* original byte count of the whole input */
+    uint64_t needed_capacity;     /* bytes this rank's slice buffer must hold (HF_ERR_CAPACITY: retry with at least this) */
+} hf_slice_info_t;
+
+typedef struct {
+    uint64_t n_total;             /* original byte count (D:243-255) */
+    uint64_t out_offset;          /* byte offset of this rank's output in the original */
+    uint64_t out_bytes;           /* bytes this rank decoded into d_out */
+    uint64_t payload_start_bit;
+    uint64_t needed_symbols;      /* symbols this rank's range holds (status 2: what the buffer must take) */
+    uint32_t max_code_bits, is_odd, last_byte;
+    uint32_t status;              /* 0 done; 1 the stream does not re-synchronise where the ranks speculated: gather it on
+                                     one rank (hf_gather_image) and hf_decompress it there; 2 an output buffer was too small.
+                                     The same on every rank. */
+} hf_shard_out_t;
+
+/* rank 0 creates the id, the caller distributes it (MPI, a file, torch.distributed, ...), every rank calls hf_comm_init */
+int hf_comm_unique_id(hf_unique_id_t *id);
+int hf_comm_init(hf_ctx *ctx, const hf_unique_id_t *id, int rank, int nranks);
+int hf_comm_destroy(hf_ctx *ctx);
+uint64_t hf_collective_count(hf_ctx *ctx);        /* NCCL calls this context has issued (bench.py) */
+
+/* d_chunk: this rank's bytes of the input (even offset, 16-byte aligned cut); d_slice: 16-byte aligned, capacity >=
+ * hf_compress_bound(chunk_bytes) + HF_SHARD_HALO + 64 is enough unless the chunk codes worse than 16 bits per byte pair
+ * under the codebook of the WHOLE input; when any rank's slice does not fit, EVERY rank returns HF_ERR_CAPACITY (the
+ * capacities travel with the bit counts) with h_info->needed_capacity set, and the job is retried as a whole.  On
+ * return d_slice[0 .. range_bytes) is this rank's part of the image and HF_SHARD_HALO bytes of the next rank's part
+ * follow it.  Synchronises once, at the end. */
+int hf_compress_sharded(hf_ctx *ctx, const uint8_t *d_chunk, uint64_t chunk_bytes, uint64_t n_total, uint32_t last_byte,
+                        uint8_t *d_slice, uint64_t capacity, hf_slice_info_t *h_info);
+/* d_slice: range_bytes of the image followed by halo_bytes (>= 16) of read-ahead (the next bytes of the image, zeros
+ * past its end); only rank 0's slice must start at image byte 0.  d_out takes this rank's part of the output
+ * (out_capacity bytes; n_total / nranks + 64 KiB is enough unless the ranges are very uneven).  Synchronises once. */
+int hf_decompress_sharded(hf_ctx *ctx, const uint8_t *d_slice, uint64_t range_bytes, uint64_t halo_bytes, uint64_t image_bytes,
+                          uint8_t *d_out, uint64_t out_capacity, hf_shard_out_t *h_out);
+/* every rank's range to rank 0's d_image (the one file; also the fall-back of status 1) */
+int hf_gather_image(hf_ctx *ctx, const uint8_t *d_slice, uint64_t first_byte, uint64_t range_bytes, uint8_t *d_image,
+                    uint64_t image_capacity);
+
+/* The phases hf_compress_sharded / hf_decompress_sharded run between their collectives, for callers with another
+ * transport (and for tests: eight contexts on one GPU emulate eight ranks).  All asynchronous except the last of each.
+ *   compress:   local (histogram of my chunk)                       -> sum d_hist_local over the ranks into d_hist_total
+ *               bits (codebook from the total; my (payload bits, slice capacity) into d_allbits[2 * rank])
+ *                                                                    -> all-gather d_allbits
+ *               pack (plan, header on rank 0, my slice, my seam record into d_recs[rank * HF_SHARD_REC_BYTES])
+ *                                                                    -> all-gather d_recs
+ *               seams (OR-merge, read-ahead; synchronises, fills h_info)
+ *   decompress: header (rank 0 copies the head of its slice into d_hdr[HF_HEADER_MAX])  -> broadcast d_hdr
+ *               sync (tables; speculative synchronisation of my range; (overflow, bits) into d_probe[2 * rank])
+ *                                                                    -> all-gather d_probe
+ *               write (my first bit from the chain; head repair; symbols out; result into d_res[4 * rank])
+ *                                                                    -> all-gather d_res
+ *               finish (checks the speculation, output offsets; synchronises, fills h_out) */
+int hf_shard_compress_local(hf_ctx *ctx, const uint8_t *d_chunk, uint64_t chunk_bytes, uint64_t *d_hist_local);
+int hf_shard_compress_bits(hf_ctx *ctx, const uint64_t *d_hist_total, const uint64_t *d_hist_local, int rank,
+                           uint64_t slice_capacity, uint64_t *d_allbits);
+int hf_shard_compress_pack(hf_ctx *ctx, const uint8_t *d_chunk, uint64_t chunk_bytes, uint64_t n_total, uint32_t last_byte,
+                           int rank, int nranks, const uint64_t *d_allbits, uint8_t *d_slice, uint64_t capacity,
+                           uint8_t *d_recs);
+int hf_shard_compress_seams(hf_ctx *ctx, uint64_t n_total, int rank, int nranks, const uint64_t *d_allbits,
+                            const uint8_t *d_recs, uint8_t *d_slice, hf_slice_info_t *h_info);
+int hf_shard_decompress_header(hf_ctx *ctx, int rank, const uint8_t *d_slice, uint64_t avail_bytes, uint8_t *d_hdr);
+int hf_shard_decompress_sync(hf_ctx *ctx, int rank, const uint8_t *d_hdr, uint64_t image_bytes, const uint8_t *d_slice,
+                             uint64_t range_bytes, uint64_t halo_bytes, uint64_t *d_probe);
+int hf_shard_decompress_write(hf_ctx *ctx, int rank, int nranks, const uint64_t *d_probe, const uint8_t *d_slice,
+                              uint64_t range_bytes, uint64_t halo_bytes, uint8_t *d_out, uint64_t out_capacity,
+                              uint64_t *d_res);
+int hf_shard_decompress_finish(hf_ctx *ctx, int rank, int nranks, const uint64_t *d_probe, const uint64_t *d_res,
+                               hf_shard_out_t *h_out);
 
 /* ---- host-buffer calls (what the CLIs and the end-to-end benchmark use) - */
 

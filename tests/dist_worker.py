@@ -27,27 +27,32 @@ def main():
               "three_bytes": cases["three_bytes"], "two_symbols_skew": cases["two_symbols_skew"],
               "single_symbol_run": cases["single_symbol_run"], "long_runs_five": cases["long_runs_five"]}
     codec = Codec(local)
-    job = ShardedCodec(codec)
+    codec.comm_init()                                   # NCCL communicator inside the context (hf_comm_init)
+    # the C-ABI driver (collectives on the context's stream, sizes on the device) and the Python restatement of the
+    # protocol over torch.distributed must produce the same slices
+    jobs = {"c-abi": ShardedCodec(codec), "python": ShardedCodec(codec, use_c=False)}
+    assert jobs["c-abi"].use_c and not jobs["python"].use_c
     ok = True
     for name, data in inputs.items():
         n = data.size
         lo, hi = shard_bounds(n, world)[rank]
         chunk = torch.from_numpy(data[lo:hi].copy()).cuda()
-        sl = job.compress(chunk, n, int(data[-1]) if n & 1 else 0)
-        image = job.gather_image(sl).cpu().numpy()
-        if rank == 0:
-            want = O.compress(data)
-            same = image.size == want.size and np.array_equal(image, want)
-            print(f"[{name}] image byte-identical to the oracle: {same} ({image.size} bytes)", flush=True)
-            ok &= same
-        back, off, n_total = job.decompress(sl)
-        piece = data[off:off + back.numel()]
-        good = n_total == n and np.array_equal(back.cpu().numpy(), piece)
-        cov = torch.tensor([back.numel()], dtype=torch.int64, device="cuda")
-        dist.all_reduce(cov)
-        good &= int(cov) == n & ~1
-        print(f"[{name}] rank {rank}: decoded {back.numel()} bytes at offset {off}: {good}", flush=True)
-        ok &= bool(good)
+        want = O.compress(data) if rank == 0 else None
+        for how, job in jobs.items():
+            sl = job.compress(chunk, n, int(data[-1]) if n & 1 else 0)
+            image = job.gather_image(sl).cpu().numpy()
+            if rank == 0:
+                same = image.size == want.size and np.array_equal(image, want)
+                print(f"[{name}/{how}] image byte-identical to the oracle: {same} ({image.size} bytes)", flush=True)
+                ok &= same
+            back, off, n_total = job.decompress(sl)
+            piece = data[off:off + back.numel()]
+            good = n_total == n and np.array_equal(back.cpu().numpy(), piece)
+            cov = torch.tensor([back.numel()], dtype=torch.int64, device="cuda")
+            dist.all_reduce(cov)
+            good &= int(cov) == n & ~1
+            print(f"[{name}/{how}] rank {rank}: decoded {back.numel()} bytes at offset {off}: {good}", flush=True)
+            ok &= bool(good)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
