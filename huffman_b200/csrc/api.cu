@@ -7,9 +7,6 @@
 #include <stdlib.h>
 #include <sys/stat.h>
 #include <sys/time.h>
-#include <dirent.h>
-
-#include <string>
 
 #include "common.cuh"
 
@@ -32,7 +29,7 @@ int ensure_ws(Ctx *c, size_t bytes)
 {
     if (bytes <= c->ws_bytes) return HF_OK;
     size_t want = bytes + (bytes >> 2);
-    if (want < (96u << 20)) want = 96u << 20;
+    if (want < (32u << 20)) want = 32u << 20;
     if (c->ws) HF_CUDA(c, cudaFree(c->ws));     // synchronises: no kernel still uses the old block
     c->ws = nullptr; c->ws_bytes = 0;
     HF_CUDA(c, cudaMalloc(&c->ws, want));
@@ -54,7 +51,7 @@ void prof_end(Ctx *c)
     c->prof_open = false;
 }
 
-static int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes)
+int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes)
 {
     if (bytes <= *have) return HF_OK;
     if (*p) HF_CUDA(c, cudaFree(*p));
@@ -64,7 +61,7 @@ static int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes)
     return HF_OK;
 }
 
-static double now_ms()
+double now_ms()
 {
     struct timeval tv;
     gettimeofday(&tv, nullptr);
@@ -115,7 +112,6 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     ok = ok && cudaMalloc(&c->d_tab, sizeof(DecodeTable)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_hist, NSYM * 8 + 256) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_scan, SCAN_BLOCKS_MAX * 8) == cudaSuccess;
-    ok = ok && ensure_ws(c, 1) == HF_OK;
     if (!ok) { hf_ctx_destroy(reinterpret_cast<hf_ctx *>(c)); return HF_ERR_CUDA; }
     *out = reinterpret_cast<hf_ctx *>(c);
     return HF_OK;
@@ -132,6 +128,7 @@ int hf_ctx_destroy(hf_ctx *ctx)
     if (c->h_pipe) cudaFreeHost(c->h_pipe);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     shard_release(c);
+    ring_release(c);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->d_in) cudaFree(c->d_in);
@@ -364,7 +361,7 @@ static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const ui
 
 // hf_compress / hf_compress_host after the histogram: codebook -> plan (sizes, start bit, capacity check: all on the
 // device) -> header -> payload; nothing waits for the host.  d_last / last_byte: see launch_header_pack.
-static int compress_async(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_last, uint32_t last_byte, uint8_t *d_file,
+extern "C++" int hf::compress_async(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_last, uint32_t last_byte, uint8_t *d_file,
                           uint64_t capacity, ShardPlan **d_plan)
 {
     Codebook *cb = reinterpret_cast<Codebook *>(c->d_cb);
@@ -378,7 +375,7 @@ static int compress_async(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t
 }
 
 // the plan after the stream has drained: the image size, or why there is no image
-static int compress_result(Ctx *c, const ShardPlan *d_plan, uint64_t capacity, uint64_t *h_file_bytes)
+extern "C++" int hf::compress_result(Ctx *c, const ShardPlan *d_plan, uint64_t capacity, uint64_t *h_file_bytes)
 {
     ShardPlan *h = reinterpret_cast<ShardPlan *>((uint8_t *)c->h_scratch + 2560);
     HF_CUDA(c, cudaMemcpyAsync(h, d_plan, sizeof(ShardPlan), cudaMemcpyDeviceToHost, c->stream));
@@ -496,7 +493,7 @@ int hf_range_overflow(hf_ctx *ctx, const uint8_t *d_range, uint64_t range_bytes,
 }
 
 // what the decode kernels report (DecWork, decode_common.cuh) sits at the start of the workspace's stage region
-static int check_decode_flags(Ctx *c)
+extern "C++" int hf::check_decode_flags(Ctx *c)
 {
     unsigned long long *h = reinterpret_cast<unsigned long long *>((uint8_t *)c->h_scratch + 3072);
     HF_CUDA(c, cudaMemcpyAsync(h, (uint8_t *)c->ws + WS_STAGE_OFFSET, 64, cudaMemcpyDeviceToHost, c->stream));
@@ -772,104 +769,6 @@ int hf_decompress_host(hf_ctx *ctx, const uint8_t *h_file, uint64_t file_bytes, 
     if (rc) return rc;
     if (info.is_odd) h_out[info.original_bytes - 1] = (uint8_t)info.last_byte;          // D:286-289
     return HF_OK;
-}
-
-// ---- program-level entry points ------------------------------------------------------
-static bool file_exists(const std::string &name)
-{   // D:222-240: a file or a directory of that name
-    FILE *fp = fopen(name.c_str(), "rb");
-    if (fp) { fclose(fp); return true; }
-    DIR *d = opendir(name.c_str());
-    if (d) { closedir(d); return true; }
-    return false;
-}
-
-int hf_archive_file(hf_ctx *ctx, const char *path)
-{
-    NEED_CTX(ctx);
-    Ctx *c = CTX(ctx);
-    FILE *f = fopen(path, "rb");
-    if (!f) {                                                   // C:325-330
-        printf("%s file does not exist\nProcess has been terminated\n", path);
-        return HF_OK;
-    }
-    fseek(f, 0, SEEK_END);
-    const uint64_t n = (uint64_t)ftell(f);
-    fseek(f, 0, SEEK_SET);
-    printf("The size of the sum of ORIGINAL files is: %llu bytes\n", (unsigned long long)n);   // C:335
-    uint8_t *h_in = nullptr, *h_out = nullptr;
-    const uint64_t bound = hf_compress_bound(n);
-    if (hf_host_alloc((void **)&h_in, n + 1) || hf_host_alloc((void **)&h_out, bound)) {
-        fclose(f);
-        if (h_in) hf_host_free(h_in);
-        return set_err(c, HF_ERR_CUDA, "hf_archive_file: pinned allocation failed");
-    }
-    size_t got = n ? fread(h_in, 1, n, f) : 0;
-    fclose(f);
-    int rc = got == n ? HF_OK : set_err(c, HF_ERR_IO, "hf_archive_file: short read");
-    uint64_t total = 0;
-    if (!rc) {
-        double t0 = now_ms();
-        rc = hf_compress_host(ctx, h_in, n, h_out, bound, &total);
-        double t1 = now_ms();
-        if (!rc) {
-            hf_cb_info_t info;
-            hf_codebook_info(ctx, c->d_cb, &info);
-            printf("Unique symbols count: %u\n", info.n_unique);                            // C:385
-            printf("Histograming, construction and Encoding took %.3f ms\n", t1 - t0);
-        }
-    }
-    if (!rc) {
-        std::string outp = std::string(path) + ".compressed";                              // C:427-429
-        FILE *o = fopen(outp.c_str(), "wb");
-        if (!o || fwrite(h_out, 1, total, o) != total) rc = set_err(c, HF_ERR_IO, "hf_archive_file: cannot write %s", outp.c_str());
-        if (o) fclose(o);
-        if (!rc) {
-            printf("The size of the COMPRESSED file is: %llu bytes\n", (unsigned long long)total);      // C:612
-            printf("Compressed file's size is [%g%%] of the original files.\n", 100.0f * (float)total / (float)n);   // C:616-619
-            if (total > n) printf("\nWARNING: The compressed file's size is larger than the sum of the originals.\n\n");
-            printf("\nCreated compressed file: %s\nCompression is complete\n", outp.c_str());  // C:629-631
-        }
-    }
-    hf_host_free(h_in);
-    hf_host_free(h_out);
-    return rc;
-}
-
-int hf_extract_file(hf_ctx *ctx, const char *path)
-{
-    NEED_CTX(ctx);
-    Ctx *c = CTX(ctx);
-    FILE *f = fopen(path, "rb");
-    if (!f) { printf("%s does not exist\n", path); return HF_OK; }      // D:59-63
-    fseek(f, 0, SEEK_END);
-    const uint64_t nb = (uint64_t)ftell(f);
-    fseek(f, 0, SEEK_SET);
-    uint8_t *h_file = nullptr, *h_out = nullptr;
-    if (hf_host_alloc((void **)&h_file, nb + 1)) { fclose(f); return set_err(c, HF_ERR_CUDA, "hf_extract_file: pinned allocation failed"); }
-    size_t got = nb ? fread(h_file, 1, nb, f) : 0;
-    fclose(f);
-    int rc = got == nb ? HF_OK : set_err(c, HF_ERR_IO, "hf_extract_file: short read");
-    uint64_t n = 0;
-    if (!rc && hf_decompressed_size_host(h_file, nb, &n)) rc = set_err(c, HF_ERR_FORMAT, "hf_extract_file: malformed header");
-    if (!rc && hf_host_alloc((void **)&h_out, n + 1)) rc = set_err(c, HF_ERR_CUDA, "hf_extract_file: pinned allocation failed");
-    if (!rc) rc = hf_decompress_host(ctx, h_file, nb, h_out, n, &n);
-    if (!rc) {
-        std::string name = "DECOMPRESSED_FILE";                                             // D:104
-        if (file_exists(name)) {                                                            // D:185-219
-            for (int k = 1; k < 10; k++) {
-                name = "DECOMPRESSED_FILE(" + std::to_string(k) + ")";
-                if (!file_exists(name)) break;
-            }
-        }
-        FILE *o = fopen(name.c_str(), "wb");
-        if (!o || (n && fwrite(h_out, 1, n, o) != n)) rc = set_err(c, HF_ERR_IO, "hf_extract_file: cannot write %s", name.c_str());
-        if (o) fclose(o);
-        if (!rc) printf("Decompression is complete\n");                                     // D:113
-    }
-    hf_host_free(h_file);
-    if (h_out) hf_host_free(h_out);
-    return rc;
 }
 
 }  // extern "C"

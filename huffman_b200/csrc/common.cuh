@@ -149,6 +149,11 @@ struct Ctx {
     int rank, nranks;
     uint64_t collectives;
     void *d_shard, *d_hist2, *d_hdr;
+    // pinned ring of the file programs (programs.cu): ring_n slots of ring_slot bytes, an event each
+    uint8_t *ring;
+    size_t ring_slot;
+    int ring_n;
+    cudaEvent_t ring_ev[4];
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
     bool prof_open;                 // a begin event is pending
@@ -238,8 +243,16 @@ int launch_range_sync(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint
 int launch_range_write(Ctx *c, const uint8_t *d_range, uint64_t range_bytes, uint64_t halo_bytes,
                        const unsigned long long *d_first_bit, const DecodeTable *d_tab, uint8_t *d_out, uint64_t out_symbols,
                        unsigned long long *d_result);
+// api.cu helpers shared with programs.cu
+int ensure_buf(Ctx *c, void **p, size_t *have, size_t bytes);
+double now_ms();
+int compress_async(Ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_last, uint32_t last_byte, uint8_t *d_file,
+                   uint64_t capacity, ShardPlan **d_plan);
+int compress_result(Ctx *c, const ShardPlan *d_plan, uint64_t capacity, uint64_t *h_file_bytes);
+int check_decode_flags(Ctx *c);
 int launch_plan_single(Ctx *c, const Codebook *d_cb, uint64_t n_total, uint64_t capacity, ShardPlan **d_plan);
 void shard_release(Ctx *c);
+void ring_release(Ctx *c);
 int launch_decompress_image(Ctx *c, const uint8_t *d_file, uint64_t file_bytes, const hf_header_info_t *d_info,
                             const DecodeTable *d_tab, uint8_t *d_out, uint64_t capacity);
 

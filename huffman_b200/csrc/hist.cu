@@ -4,8 +4,8 @@
 // Design (B200): one persistent CTA per SM holds ALL 65,536 bins in shared memory as
 // packed 16-bit counters (2 per 32-bit word, 128 KiB of the SM's 227 KiB), so every
 // count is one shared-memory atomic and the input is read exactly once with 128-bit
-// streaming loads.  A 16-bit field that reaches 0x8000 is spilled (its 0x8000 moved to
-// the 64-bit global bin) by the one thread that saw the crossing, so fields never wrap.
+// streaming loads.  A 16-bit field that reaches SPILL (bit 14) is spilled (SPILL counts moved
+// to the 64-bit global bin) by the one thread that saw the crossing, so fields never wrap.
 // The bin index is XOR-folded (low byte ^= high byte, an involution) so that text-like
 // inputs, whose first bytes cluster, still spread over the 32 banks.
 // CTA partials go to global memory with coalesced stores and a second small kernel
@@ -23,7 +23,14 @@ constexpr uint64_t HIST_SMALL_BYTES = 1u << 18;
 
 __device__ __forceinline__ uint32_t fold(uint32_t sym) { return sym ^ (sym >> 8); }   // involution on 16 bits
 
-// adds n (< 0x2000) to the bin of `sym`
+// The spill is two steps: the add that sets the field's bit 14, then the subtraction of SPILL.  Other threads keep adding
+// to the field in between; it stays inside its 16 bits as long as fewer than 0x10000 - 2 * SPILL + 1 = 32,769 counts land
+// in that window — an add is at most 256 (a warp's hot symbol over one step) and the window is a few instructions of the
+// thread that saw the crossing, so the 1024 threads of the CTA would have to deliver over a hundred such adds each within it.
+// (Round 1 spilled at bit 15, which left a window of 0x7F00 counts: the advisor's finding.)
+constexpr uint32_t SPILL = 0x4000u;
+
+// adds n (<= 256) to the bin of `sym`
 __device__ __forceinline__ void count_sym(uint32_t *sh, unsigned long long *ghist, uint32_t sym, uint32_t n = 1)
 {
     uint32_t ix = fold(sym);
@@ -31,9 +38,9 @@ __device__ __forceinline__ void count_sym(uint32_t *sh, unsigned long long *ghis
     uint32_t sa = (ix >> 11) & 16u;                 // field select: 0 or 16
     uint32_t inc = n << sa;
     uint32_t old = atomicAdd(&sh[w], inc);
-    if (((old + inc) & ~old) & (0x8000u << sa)) {   // my add set bit 15 of the field
-        atomicSub(&sh[w], 0x8000u << sa);
-        atomicAdd(&ghist[sym], 0x8000ull);
+    if (((old + inc) & ~old) & (SPILL << sa)) {     // my add set bit 14 of the field
+        atomicSub(&sh[w], SPILL << sa);
+        atomicAdd(&ghist[sym], (unsigned long long)SPILL);
     }
 }
 

@@ -26,7 +26,7 @@ GOLD = os.path.join(ROOT, "tests", "golden", "inputs")
 
 def run(cmd, cwd):
     t0 = time.perf_counter()
-    p = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True)
+    p = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, env=dict(os.environ, HF_TIMING="1"))
     return time.perf_counter() - t0, p.stdout + p.stderr
 
 
@@ -83,11 +83,12 @@ def main():
             w, out = run([ours_arch, src], td)
             img = np.fromfile(src + ".compressed", dtype=np.uint8)
             same = img.size == ref_img.size and np.array_equal(img, ref_img)
-            m = re.search(r"took ([0-9.]+) ms", out)
-            rows.append(("bin/archive (this repo)", w * 1e3, f"host-buffer call {m.group(1) if m else '?'} ms; image byte-identical to the reference's: {same}"))
-            w, _ = run([ours_extr, src + ".compressed"], td)
+            tm = " | ".join(re.findall(r"\[hf timing\] (.*)", out))
+            rows.append(("bin/archive (this repo)", w * 1e3, f"image byte-identical to the reference's: {same}; {tm}"))
+            w, out = run([ours_extr, src + ".compressed"], td)
             ok = np.array_equal(np.fromfile(os.path.join(td, "DECOMPRESSED_FILE"), dtype=np.uint8), data)
-            rows.append(("bin/extract (this repo)", w * 1e3, f"round trip {'ok' if ok else 'FAILED'}"))
+            tm = " | ".join(re.findall(r"\[hf timing\] (.*)", out))
+            rows.append(("bin/extract (this repo)", w * 1e3, f"round trip {'ok' if ok else 'FAILED'}; {tm}"))
             # the data path alone, device buffers, CUDA events
             d = torch.from_numpy(data).cuda()
             out_img = torch.empty(codec.compress_bound(n), dtype=torch.uint8, device="cuda")

@@ -563,6 +563,74 @@ def test_archive_extract_programs(oracle, romeo):
         assert subprocess.run([extract], cwd=td, capture_output=True).returncode == 1      # D:51-56
 
 
+def test_archive_stdout_has_the_reference_lines(oracle, romeo):
+    """a script that greps the reference's progress lines and timers must keep working (C:335, C:385, C:399, h:704-705,
+    h:780-782, C:490, C:545, C:571, C:593, C:611-631): same lines, same order, numbers aside; compared with the
+    UNMODIFIED reference GPU archive run here on the same file"""
+    import re
+    ref = oracle.ref_binary("ref_archive_gpu")
+    if ref is None:
+        pytest.skip("oracle/_ref/ref_archive_gpu not built")
+    archive = os.path.join(ROOT, "bin", "archive")
+
+    def lines(exe, td):
+        p = os.path.join(td, "romeo.txt")
+        romeo.tofile(p)
+        r = subprocess.run([exe, p], cwd=td, capture_output=True, text=True, check=True)
+        out = []
+        for ln in r.stdout.splitlines():
+            if ln.startswith("og/2"):                       # the reference's stray device printf (C:202-204)
+                continue
+            ln = ln.replace(td, "<dir>")
+            out.append(re.sub(r"[-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?", "#", ln))
+        return out, np.fromfile(p + ".compressed", dtype=np.uint8)
+
+    with tempfile.TemporaryDirectory() as ta, tempfile.TemporaryDirectory() as tb:
+        ours, img_ours = lines(archive, ta)
+        theirs, img_ref = lines(ref, tb)
+    assert np.array_equal(img_ours, img_ref)
+    assert ours == theirs, "\n".join(["ours:"] + ours + ["reference:"] + theirs)
+
+
+def test_archive_extract_side_index_file(oracle):
+    """HF_SIDE_INDEX=1 archive f -> f.compressed + f.compressed.idx; extract uses the index when it is there and valid,
+    and decodes without it when it is absent, truncated or belongs to another image"""
+    archive, extract = os.path.join(ROOT, "bin", "archive"), os.path.join(ROOT, "bin", "extract")
+    data = synth.mixed(40 << 20, seg_bytes=4 << 20)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "in.bin")
+        data.tofile(p)
+        env = dict(os.environ, HF_SIDE_INDEX="1")
+        subprocess.run([archive, p], cwd=td, capture_output=True, text=True, check=True, env=env)
+        image = np.fromfile(p + ".compressed", dtype=np.uint8)
+        assert np.array_equal(image, oracle.compress(data))                  # the image is the same bytes with or without
+        idx = p + ".compressed.idx"
+        assert os.path.getsize(idx) > 64
+
+        def run_extract(extra_env=None):
+            out = os.path.join(td, "DECOMPRESSED_FILE")
+            if os.path.exists(out):
+                os.remove(out)
+            r = subprocess.run([extract, p + ".compressed"], cwd=td, capture_output=True, text=True, check=True,
+                               env=dict(os.environ, HF_TIMING="1", **(extra_env or {})))
+            assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
+            return r.stderr
+
+        assert "(side index)" in run_extract()
+        assert "(side index)" not in run_extract({"HF_SIDE_INDEX": "0"})      # switched off
+        raw = np.fromfile(idx, dtype=np.uint8)
+        raw[: raw.size // 2].tofile(idx)                                       # truncated: ignored
+        run_extract()
+        other = synth.zipf1g(3 << 20)
+        q = os.path.join(td, "other.bin")
+        other.tofile(q)
+        subprocess.run([archive, q], cwd=td, capture_output=True, check=True, env=env)
+        os.replace(q + ".compressed.idx", idx)                                 # another image's index: ignored
+        run_extract()
+        os.remove(idx)
+        assert "(side index)" not in run_extract()                             # absent
+
+
 def test_compress_unaligned_input_and_ragged_sizes(codec, oracle):
     # the encoder works on 1 KiB units of a 16-byte aligned input; any 2-byte aligned input of any size must give
     # the same bytes (scalar loads, ragged last unit, a last unit that owns no word of the stream)
