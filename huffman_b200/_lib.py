@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
+# HF_LIB_PATH: development aid (A/B timing of builds with other -D flags, scripts/build_variant.sh); still no fallback
+LIB_PATH = os.environ.get("HF_LIB_PATH") or os.path.join(_HERE, "libhuffb200.so")
 
 HF_OK = 0
 ERR_NAMES = {

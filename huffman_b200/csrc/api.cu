@@ -103,6 +103,12 @@ int hf_ctx_create(hf_ctx **out, int device, void *stream)
     c->stream = (cudaStream_t)stream;                   // NULL = the legacy default stream, as the reference uses
     c->own_stream = false;
     c->nranks = 1;
+    {   // development aids for A/B timing: HF_WRITE_KERNEL=3 / 4 gives every chunk to one write kernel, HF_WRITE_SPLIT moves the split
+        const char *e = getenv("HF_WRITE_KERNEL");
+        c->write_kernel = e ? atoi(e) : 0;
+        e = getenv("HF_WRITE_SPLIT");
+        c->write_split = e ? (uint32_t)atoi(e) : WRITE_SPLIT_DEFAULT;
+    }
     bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_pipe, PIPE_SLOTS * 8) == cudaSuccess;

@@ -144,6 +144,8 @@ struct Ctx {
     // kernels whose dynamic shared-memory limit has been raised on THIS context's device (a process may hold
     // contexts on several GPUs; the attribute is per device)
     bool smem_attr[8];
+    int write_kernel;               // development aid (environment HF_WRITE_KERNEL=3 / 4): one write kernel for every chunk
+    uint32_t write_split;           // symbols per chunk from which a chunk is dec_write4_kernel's (HF_WRITE_SPLIT)
     // sharded job (sharded.cu): NCCL communicator, device state, summed histogram, header staging
     void *comm;
     int rank, nranks;
@@ -161,7 +163,9 @@ struct Ctx {
     cudaEvent_t *prof_ev;           // 2 * PROF_CAP events, created on first enable
     const char **prof_name;         // PROF_CAP static strings
 };
-enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE, ATTR_INDEX };
+enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE, ATTR_INDEX, ATTR_WRITE4 };
+// chunks (16 KiB of payload) with this many code words or more (under ~9 bits each) are written by dec_write4_kernel
+constexpr uint32_t WRITE_SPLIT_DEFAULT = 131072 / 9;
 constexpr uint32_t PROF_CAP = 8192;
 constexpr uint32_t PIPE_SLOTS = 4096;
 constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload

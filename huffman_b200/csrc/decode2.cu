@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1)
 dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
                   const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
                   unsigned long long c0, unsigned long long c1,
-                  uint16_t *__restrict__ out, uint32_t check, uint32_t upw)
+                  uint16_t *__restrict__ out, uint32_t check, uint32_t upw, uint32_t dense_min)
 {
     extern __shared__ __align__(16) uint32_t w3_smem[];
     constexpr uint32_t WIN = W3_WIN;
@@ -644,6 +644,14 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint16_t *sout = s_leaves + NSYM + wid * (WIN + 8);                         // this warp's window
+    if (dense_min != 0xFFFFFFFFu) {     // every chunk of this CTA is dec_write4_kernel's: leave before the planes load
+        const unsigned long long upc = (DEC_THREADS / 32) / upw;                // runs per chunk
+        bool any = false;
+        for (unsigned long long run = (unsigned long long)blockIdx.x * W3_WARPS + wid + (unsigned long long)lane * gridDim.x * W3_WARPS;
+             run < (c1 - c0) * upc && !any; run += 32ull * gridDim.x * W3_WARPS)
+            any = L.chunkCnt[c0 + run / upc] < dense_min;
+        if (!__syncthreads_or(any)) return;
+    }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
         uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
@@ -667,6 +675,7 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
         const uint32_t u0 = (uint32_t)(ug0 % UPC);
         const unsigned long long cbase = L.chunkBase[c];
         if (cbase >= n_symbols || (c + 1) * DEC_THREADS <= head_sub) continue;     // nothing left to write / before the first code word
+        if (L.chunkCnt[c] >= dense_min) continue;       // a chunk of short code words: dec_write4_kernel's
         uint32_t ninf = L.info[c * DEC_THREADS + 32 * u0 + lane];
         uint32_t nr[9];
         load_sub_raw(nr, frame, frame_bytes, c, 32 * u0 + lane, lane);
@@ -784,6 +793,221 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             if (cnt && my_end == off + cnt && !last && ((nxt >> 6) == 0 || pos < SUB_BITS || pos - SUB_BITS != (nxt & 63u))) bad = 1;
         }
         base += unit_total;
+        }
+    }
+    if (bad) atomicExch(&work->flags[1], 1ull);
+}
+
+// ---- bulk copies (TMA, non-tensor form) of the table planes into shared memory ---------------------
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk global -> shared copies; everybody waits
+// on the barrier's phase.  Replaces per-thread LDG.128 + STS.128 staging loops (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+constexpr uint32_t BULK_PIECE = 32768;                  // bytes per cp.async.bulk
+// thread 0 of the CTA: src (16-byte aligned, `bytes` a multiple of 16) -> shared address dst, completion on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    for (uint32_t o = 0; o < bytes; o += BULK_PIECE)
+        bulk_g2s(dst + o, reinterpret_cast<const uint8_t *>(src) + o, min(BULK_PIECE, bytes - o), bar);
+}
+
+// -------------------------------------------------------------------------------------------------
+// dec_write4_kernel: every WARP decodes one chunk, every LANE a contiguous span of 16 subsequences (512 bytes of
+// payload) into a contiguous run of output symbols.  dec_write3_kernel gives a lane ONE subsequence of a unit and
+// walks it in phases of 64 bits (the subsequence sits in registers, which need static indices): lanes wait for each
+// other at every phase end, and a unit of short code words does not fit the warp's staging window, so only a third of
+// the lanes work at a time.  Here
+//   * the lane streams its span through a private shared-memory row (9 words, column-major: a lane stays in its own
+//     bank), so the window of a code word is two loads by a dynamic index and the lanes wait for each other once per
+//     subsequence (256 bits), not four times;
+//   * the symbols go to a private 16-entry ring (column-major u16) and leave, eight at a time, as ONE aligned 16-byte
+//     global store per lane: no staging window, no window passes, no per-unit scan.  The lanes run in lock step, so
+//     after a block of eight steps every active lane has eight symbols pending and the stores of a warp issue together;
+//     the two partial vectors at the ends of a lane's run (once per 4096 bits) leave a symbol at a time;
+//   * the planes arrive by bulk copies (cp.async.bulk + mbarrier), the payload by 32-byte loads one subsequence ahead.
+// Nothing is shared between lanes after the offset scan: no barrier of any kind inside the chunk loop.
+// Shared memory: t14 64 KiB | leaves 128 KiB | rings 1 KiB per warp | rows 1152 B per warp | the mbarrier.
+#ifndef W4_WARPS
+#define W4_WARPS 16
+#endif
+constexpr int W4_THREADS = W4_WARPS * 32;
+constexpr uint32_t W4_LEAVES = 4u << MICRO_K;                   // offsets inside the dynamic shared memory
+constexpr uint32_t W4_RINGS = W4_LEAVES + NSYM * 2;             // a multiple of 1024
+constexpr uint32_t W4_ROWS = W4_RINGS + W4_WARPS * 1024u;
+constexpr uint32_t W4_BAR = W4_ROWS + W4_WARPS * (ROW4_WORDS * ROW4_STRIDE);
+constexpr size_t W4_SMEM = W4_BAR + 16;
+static_assert(W4_RINGS % 1024 == 0, "the ring address is formed by OR");
+static_assert(W4_SMEM <= 232448, "dec_write4: shared memory");
+constexpr uint32_t RING_STRIDE = 64;                            // bytes between consecutive symbols of a lane's ring
+constexpr uint32_t RING_MASK = 15u * RING_STRIDE;
+
+__global__ void __launch_bounds__(W4_THREADS, 1)
+dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_bytes,
+                  const DecodeTable *__restrict__ tab, DecWork *work, unsigned long long nch,
+                  unsigned long long c0, unsigned long long c1, uint16_t *__restrict__ out, uint32_t dense_min)
+{
+    extern __shared__ __align__(1024) uint8_t w4_smem[];
+    if (tab->single_sym) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t a0 = opaque_shared_addr(w4_smem);
+    if (a0 & 1023u) __trap();                           // the ring address below is base | offset
+    {   // nothing of mine among this CTA's chunks (the usual case on data of long code words): leave before the planes load
+        DecLayout L0(work, nch);
+        bool any = false;
+        for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * W4_WARPS + wid + (unsigned long long)lane * gridDim.x * W4_WARPS;
+             c < c1 && !any; c += 32ull * gridDim.x * W4_WARPS)
+            any = L0.chunkCnt[c] >= dense_min;
+        if (!__syncthreads_or(any)) return;
+    }
+    const uint32_t bar = a0 + W4_BAR;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (4u << MICRO_K) + NSYM * 2);
+        bulk_load(a0, tab->t14, 4u << MICRO_K, bar);
+        bulk_load(a0 + W4_LEAVES, tab->leaves, NSYM * 2, bar);
+    }
+    const unsigned long long F0 = work->start[0], n_symbols = work->start[1];
+    const unsigned long long head_sub = F0 / SUB_BITS;  // the subsequence that holds the first code word
+    const uint32_t head_pos = (uint32_t)(F0 % SUB_BITS);
+    DecLayout L(work, nch);
+    const uint32_t t14_a = a0, lv_a = a0 + W4_LEAVES;
+    const uint32_t ring_a = a0 + W4_RINGS + wid * 1024u + lane * 2u;
+    const uint32_t row_a = a0 + W4_ROWS + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
+    const uint32_t k2shift = 32u - tab->k2;
+    __syncthreads();                                    // the barrier is initialised
+    mbar_wait(bar, 0);                                  // planes loaded; the warps are on their own from here
+    uint32_t bad = 0;
+    for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * W4_WARPS + wid; c < c1;
+         c += (unsigned long long)gridDim.x * W4_WARPS) {
+        const unsigned long long cbase = L.chunkBase[c];
+        if (cbase >= n_symbols || (c + 1) * DEC_THREADS <= head_sub) continue;     // nothing left to write / before the first code word
+        if (L.chunkCnt[c] < dense_min) continue;        // a chunk of long code words: dec_write3_kernel's
+        // my 16 records, my symbols, where they go
+        uint32_t r8[8];
+        {
+            const uint4 *ip = reinterpret_cast<const uint4 *>(L.info + c * DEC_THREADS);
+            const uint4 a = ip[2 * lane], d = ip[2 * lane + 1];
+            r8[0] = a.x; r8[1] = a.y; r8[2] = a.z; r8[3] = a.w; r8[4] = d.x; r8[5] = d.y; r8[6] = d.z; r8[7] = d.w;
+        }
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tot += ((r8[i] & 0xFFFFu) >> 6) + (r8[i] >> 22);
+        uint32_t x = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        const unsigned long long o0 = cbase + (x - tot);            // index of my first symbol
+        const uint32_t mine = o0 >= n_symbols ? 0u : (uint32_t)min((unsigned long long)tot, n_symbols - o0);   // garbage past the end is dropped
+        uint16_t *gp = out + o0;
+        const uint32_t i0 = (uint32_t)((uintptr_t)gp >> 1) & 7u;    // ring slot s <-> gp[s], gp 16-byte aligned
+        gp -= i0;
+        // j: ring position of my next symbol, in units of RING_STRIDE (slot = j / 64 mod 16); fl: first slot not stored
+        uint32_t j = i0 * RING_STRIDE, fl = 0;
+        const uint32_t jtot = (i0 + mine) * RING_STRIDE;
+        const unsigned long long sub0 = c * DEC_THREADS + (unsigned long long)lane * LANE_SUBS;
+        const uint32_t head_k = (head_sub >= sub0 && head_sub < sub0 + LANE_SUBS) ? (uint32_t)(head_sub - sub0) : 0xFFFFu;
+        const unsigned long long span_byte0 = sub0 * (SUB_BITS / 8);
+        const bool live = mine != 0;
+        uint4 na, nd;
+        uint32_t nnext = 0;
+        if (live) load_sub_raw4(na, nd, nnext, frame, frame_bytes, span_byte0);
+#pragma unroll 1
+        for (uint32_t k = 0; k < LANE_SUBS; k++) {
+            const uint32_t rec = r8[0] & 0xFFFFu;
+#pragma unroll
+            for (int i = 0; i < 7; i++) r8[i] = __funnelshift_r(r8[i], r8[i + 1], 16);
+            r8[7] >>= 16;
+            if (!__any_sync(0xFFFFFFFFu, j < jtot)) break;
+            if (live) {
+                sts32(row_a + 0 * ROW4_STRIDE, bswap32(na.x)); sts32(row_a + 1 * ROW4_STRIDE, bswap32(na.y));
+                sts32(row_a + 2 * ROW4_STRIDE, bswap32(na.z)); sts32(row_a + 3 * ROW4_STRIDE, bswap32(na.w));
+                sts32(row_a + 4 * ROW4_STRIDE, bswap32(nd.x)); sts32(row_a + 5 * ROW4_STRIDE, bswap32(nd.y));
+                sts32(row_a + 6 * ROW4_STRIDE, bswap32(nd.z)); sts32(row_a + 7 * ROW4_STRIDE, bswap32(nd.w));
+                sts32(row_a + 8 * ROW4_STRIDE, bswap32(nnext));
+                if (k + 1 < LANE_SUBS) load_sub_raw4(na, nd, nnext, frame, frame_bytes, span_byte0 + 32ull * (k + 1));
+            }
+            const uint32_t cnt = rec >> 6;
+            uint32_t pos = k == head_k ? head_pos : (rec & 63u);
+            const uint32_t jend = min(j + cnt * RING_STRIDE, jtot);
+            while (j < jend) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    if (j < jend) {
+                        const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));     // word (pos / 32) mod 8 of my row
+                        const uint32_t win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
+                        const uint32_t e14 = lds32(t14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
+                        uint32_t len, sym;
+                        if (e14 & MICRO_FLAG) {
+                            uint32_t leaf;
+                            micro_decode(e14, win, len, leaf);
+                            sym = lds16(lv_a + 2u * leaf);
+                        } else {
+                            len = (e14 >> 1) & 0x7Fu;
+                            sym = e14 >> 16;
+                            if (len == 0) {
+                                uint32_t e = __ldg(tab->flat2 + (win >> k2shift));
+                                if (e == 0) {
+                                    e = slow_decode(tab, frame, frame_bytes, (sub0 + k) * SUB_BITS + pos);
+                                    bad |= e >> 31;
+                                }
+                                len = e & 0x7Fu;
+                                sym = (e >> 8) & 0xFFFFu;
+                            }
+                        }
+                        sts16(ring_a | (j & RING_MASK), sym);
+                        j += RING_STRIDE;
+                        pos += len;
+                    }
+                }
+                if (j - fl >= 8 * RING_STRIDE) {
+                    // eight symbols from ring slots (fl / 64 mod 16) ..: one aligned vector (the first one of my run may
+                    // begin before my first symbol: a symbol at a time then)
+                    const uint32_t ra = ring_a | (fl & (8u * RING_STRIDE));
+                    uint32_t s8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; t++) s8[t] = lds16(ra + t * RING_STRIDE);
+                    uint16_t *dst = gp + (fl / RING_STRIDE);
+                    if (fl == 0 && i0 != 0) {
+#pragma unroll
+                        for (int t = 1; t < 8; t++) if ((uint32_t)t >= i0) dst[t] = (uint16_t)s8[t];
+                    } else {
+#ifdef W4_EXP_NOSTORE
+                        if (s8[0] == 0x12345 && s8[7] == 0x54321)
+#endif
+                        st_stream_v4(dst, make_uint4(s8[0] | (s8[1] << 16), s8[2] | (s8[3] << 16), s8[4] | (s8[5] << 16), s8[6] | (s8[7] << 16)));
+                    }
+                    fl += 8 * RING_STRIDE;
+                }
+            }
+        }
+        // what is left of my run: fewer than eight symbols, one at a time
+        {
+            const uint32_t ra = ring_a | (fl & (8u * RING_STRIDE));
+            const uint32_t s_lo = fl / RING_STRIDE, s_hi = j / RING_STRIDE;
+#pragma unroll
+            for (uint32_t t = 0; t < 8; t++) {
+                const uint32_t s = s_lo + t;
+                if (s >= i0 && s < s_hi) gp[s] = (uint16_t)lds16(ra + t * RING_STRIDE);
+            }
         }
     }
     if (bad) atomicExch(&work->flags[1], 1ull);
@@ -1099,6 +1323,24 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
         HF_CUDA(c, cudaFuncSetAttribute(dec_write3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         c->smem_attr[ATTR_WRITE] = true;
     }
+    // Chunks of short code words (dense_min symbols or more in their 16 KiB) go to dec_write4_kernel, the others to
+    // dec_write3_kernel: both kernels run over the range and each skips the other's chunks.  Records that came from a
+    // side index are checked by dec_write3_kernel only.
+    uint32_t dense_min = check ? 0xFFFFFFFFu : c->write_split;
+    if (c->write_kernel == 3) dense_min = 0xFFFFFFFFu;
+    if (c->write_kernel == 4 && !check) dense_min = 0;
+    if (dense_min != 0xFFFFFFFFu) {
+        if (!c->smem_attr[ATTR_WRITE4]) {
+            HF_CUDA(c, cudaFuncSetAttribute(dec_write4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W4_SMEM));
+            c->smem_attr[ATTR_WRITE4] = true;
+        }
+        unsigned long long grid = (c1 - c0 + W4_WARPS - 1) / W4_WARPS;
+        if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
+        HF_PROF(c, "dec_write4_kernel");
+        dec_write4_kernel<<<(unsigned)grid, W4_THREADS, W4_SMEM, c->stream>>>(frame, frame_bytes, d_tab, work, nch, c0, c1, out, dense_min);
+        HF_LAUNCH_CHECK(c);
+        if (dense_min == 0) return HF_OK;
+    }
     // units per run: a whole chunk per warp when that still gives every warp of the machine 16 runs or more (fewer
     // runs per warp leave the warps that got one less idle at the end)
     uint32_t upw = DEC_THREADS / 32;
@@ -1107,7 +1349,7 @@ int launch_write2(Ctx *c, const uint8_t *frame, unsigned long long frame_bytes,
     unsigned long long grid = (nruns + W3_WARPS - 1) / W3_WARPS;
     if (grid > (unsigned long long)c->sm_count) grid = c->sm_count;
     HF_PROF(c, "dec_write3_kernel");
-    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, d_tab, work, nch, c0, c1, out, check ? 1u : 0u, upw);
+    dec_write3_kernel<<<(unsigned)grid, W3_THREADS, W3_SMEM, c->stream>>>(frame, frame_bytes, d_tab, work, nch, c0, c1, out, check ? 1u : 0u, upw, dense_min);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
