@@ -39,6 +39,7 @@ struct Codebook {
 };
 static_assert(offsetof(Codebook, p16) % 16 == 0, "encoder planes must be 16-byte aligned");
 static_assert(offsetof(Codebook, p8) == offsetof(Codebook, p16) + NSYM * 2, "encoder planes must be contiguous");
+static_assert(offsetof(Codebook, lenf) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- device-resident decode tables (hf_decode_table_bytes) ------------------------
 // Level 1: K1-bit direct table (copied to shared memory by the decode kernels).
@@ -100,6 +101,9 @@ struct DecodeTable {
     alignas(16) uint8_t lenflat[1u << FLAT_MAX];
     alignas(16) uint32_t flat2[1u << FLAT_MAX];
 };
+
+static_assert(offsetof(DecodeTable, leaves) == offsetof(DecodeTable, t14) + (4u << MICRO_K), "t14 and leaves are loaded by one bulk copy");
+static_assert(offsetof(DecodeTable, t14) % 16 == 0 && offsetof(DecodeTable, d14) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- where a slice of the image lies ---------------------------------------------------------------
 // Computed on the device (sharded.cu shard_plan_kernel) from the codebook's table size and the payload bit counts of
@@ -285,6 +289,52 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
+
+// ---- bulk copies (TMA, non-tensor form) of the table planes into shared memory ---------------------
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk global -> shared copies; everybody waits
+// on the barrier's phase.  Replaces per-thread LDG.128 + STS.128 staging loops (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+constexpr uint32_t BULK_PIECE = 32768;                  // bytes per cp.async.bulk
+// thread 0 of the CTA: src (16-byte aligned, `bytes` a multiple of 16) -> shared address dst, completion on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    for (uint32_t o = 0; o < bytes; o += BULK_PIECE)
+        bulk_g2s(dst + o, reinterpret_cast<const uint8_t *>(src) + o, min(BULK_PIECE, bytes - o), bar);
+}
+
+// All threads of the CTA: the planes [src, src + bytes) land at shared address dst; `bar` = shared address of 8 bytes
+// (8-byte aligned) for the mbarrier.  Contains a CTA barrier; one use per kernel (phase 0 of the barrier).
+__device__ __forceinline__ void cta_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, bytes);
+        bulk_load(dst, src, bytes, bar);
+    }
+    __syncthreads();                                    // the barrier is initialised
+    mbar_wait(bar, 0);
+}
 #endif
 
 }  // namespace hf

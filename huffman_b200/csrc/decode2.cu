@@ -50,7 +50,9 @@ constexpr int W3_THREADS = W3_WARPS * 32;
 #endif
 // output staging window of one warp (symbols, multiple of 8): what is left of the SM's 227 KiB beside the planes
 constexpr uint32_t W3_WIN = (((232448u - (4u << MICRO_K) - NSYM * 2 - 64u) / W3_WARPS) / 2 - 8) & ~7u;
-constexpr size_t W3_SMEM = (4u << MICRO_K) + NSYM * 2 + (size_t)W3_WARPS * (W3_WIN + 8) * 2;
+constexpr uint32_t W3_BAR = (4u << MICRO_K) + NSYM * 2 + W3_WARPS * (W3_WIN + 8) * 2;    // the mbarrier of the plane load
+constexpr size_t W3_SMEM = W3_BAR + 16;
+static_assert(W3_SMEM <= 232448, "dec_write3: shared memory");
 
 // ---- planes ------------------------------------------------------------------------------------
 // (sym << 8) | len of the code word that is a prefix of the left-aligned window, from t1 / t2; 0 when
@@ -307,7 +309,8 @@ constexpr uint32_t REC4_WORDS = LANE_SUBS / 2;                  // 16 u16 record
 constexpr uint32_t ROW4_STRIDE = 32 * 4;                        // bytes between consecutive words of a lane
 constexpr uint32_t REC4_STRIDE = 32 * 2;                        // bytes between consecutive records of a lane
 constexpr uint32_t S4_TAB_BYTES = 4u << MICRO_K;                // the d14 plane
-constexpr size_t S4_SMEM = S4_TAB_BYTES + (size_t)S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;
+constexpr uint32_t S4_BAR = S4_TAB_BYTES + S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;    // the mbarrier of the plane load
+constexpr size_t S4_SMEM = S4_BAR + 16;
 static_assert(GROUP_CHUNKS == 1, "dec_sync4: a warp converges on one chunk");
 
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
@@ -508,10 +511,8 @@ __device__ __forceinline__ void sync_chunk(const Sync4Ctx &S, uint32_t row_a, ui
 __device__ __forceinline__ void sync4_setup(uint32_t *smem, const DecodeTable *tab, uint32_t &d14_a, uint32_t &row_a, uint32_t &rec_a)
 {
     const uint32_t tid = threadIdx.x;
-    const uint4 *src = reinterpret_cast<const uint4 *>(tab->d14);           // lengths only
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (uint32_t i = tid; i < S4_TAB_BYTES / 16; i += S4_THREADS) dst[i] = __ldg(src + i);
     d14_a = opaque_shared_addr(smem);
+    cta_bulk_load(d14_a, tab->d14, S4_TAB_BYTES, d14_a + S4_BAR);          // lengths only; one bulk copy, no per-thread staging
     const uint32_t wid = tid >> 5, lane = tid & 31;
     row_a = d14_a + S4_TAB_BYTES + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
     rec_a = d14_a + S4_TAB_BYTES + S4_WARPS * (ROW4_WORDS * ROW4_STRIDE) + wid * (LANE_SUBS * REC4_STRIDE) + lane * 2u;
@@ -652,15 +653,10 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             any = L.chunkCnt[c0 + run / upc] < dense_min;
         if (!__syncthreads_or(any)) return;
     }
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t14);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_t14);
-        for (uint32_t i = tid; i < (4u << MICRO_K) / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
-        src = reinterpret_cast<const uint4 *>(tab->leaves);
-        dst = reinterpret_cast<uint4 *>(s_leaves);
-        for (uint32_t i = tid; i < NSYM * 2 / 16; i += W3_THREADS) dst[i] = __ldg(src + i);
+    {   // t14 and leaves are neighbours in the table and in shared memory: one bulk copy (192 KiB)
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(w3_smem);
+        cta_bulk_load(a0, tab->t14, (4u << MICRO_K) + NSYM * 2, a0 + W3_BAR);
     }
-    __syncthreads();
     const uint32_t k2shift = 32u - tab->k2;
     uint32_t bad = 0;
     constexpr uint32_t UPC = DEC_THREADS / 32;          // units per chunk
@@ -798,39 +794,6 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     if (bad) atomicExch(&work->flags[1], 1ull);
 }
 
-// ---- bulk copies (TMA, non-tensor form) of the table planes into shared memory ---------------------
-// One thread arms an mbarrier with the byte count and issues cp.async.bulk global -> shared copies; everybody waits
-// on the barrier's phase.  Replaces per-thread LDG.128 + STS.128 staging loops (SASS: UBLKCP + SYNCS).
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-constexpr uint32_t BULK_PIECE = 32768;                  // bytes per cp.async.bulk
-// thread 0 of the CTA: src (16-byte aligned, `bytes` a multiple of 16) -> shared address dst, completion on `bar`
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    for (uint32_t o = 0; o < bytes; o += BULK_PIECE)
-        bulk_g2s(dst + o, reinterpret_cast<const uint8_t *>(src) + o, min(BULK_PIECE, bytes - o), bar);
-}
-
 // -------------------------------------------------------------------------------------------------
 // dec_write4_kernel: every WARP decodes one chunk, every LANE a contiguous span of 16 subsequences (512 bytes of
 // payload) into a contiguous run of output symbols.  dec_write3_kernel gives a lane ONE subsequence of a unit and
@@ -879,13 +842,6 @@ dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             any = L0.chunkCnt[c] >= dense_min;
         if (!__syncthreads_or(any)) return;
     }
-    const uint32_t bar = a0 + W4_BAR;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (4u << MICRO_K) + NSYM * 2);
-        bulk_load(a0, tab->t14, 4u << MICRO_K, bar);
-        bulk_load(a0 + W4_LEAVES, tab->leaves, NSYM * 2, bar);
-    }
     const unsigned long long F0 = work->start[0], n_symbols = work->start[1];
     const unsigned long long head_sub = F0 / SUB_BITS;  // the subsequence that holds the first code word
     const uint32_t head_pos = (uint32_t)(F0 % SUB_BITS);
@@ -894,8 +850,7 @@ dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     const uint32_t ring_a = a0 + W4_RINGS + wid * 1024u + lane * 2u;
     const uint32_t row_a = a0 + W4_ROWS + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
     const uint32_t k2shift = 32u - tab->k2;
-    __syncthreads();                                    // the barrier is initialised
-    mbar_wait(bar, 0);                                  // planes loaded; the warps are on their own from here
+    cta_bulk_load(a0, tab->t14, (4u << MICRO_K) + NSYM * 2, a0 + W4_BAR);     // t14 | leaves; the warps are on their own from here
     uint32_t bad = 0;
     for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * W4_WARPS + wid; c < c1;
          c += (unsigned long long)gridDim.x * W4_WARPS) {

@@ -31,6 +31,7 @@ constexpr uint32_t UNIT_SYMS = 512;
 constexpr uint32_t GROUP_UNITS = 32;
 constexpr uint32_t GROUP_SYMS = UNIT_SYMS * GROUP_UNITS;            // 16,384
 constexpr int BITS_THREADS = 512;
+constexpr size_t BITS_SMEM = NSYM + 16;                              // lenf plane + the mbarrier of its load
 #ifndef HF_E2_WARPS
 #define HF_E2_WARPS 20
 #endif
@@ -38,7 +39,8 @@ constexpr int E2_WARPS = HF_E2_WARPS;
 constexpr int E2_THREADS = E2_WARPS * 32;
 constexpr uint32_t E2_PLANE_BYTES = NSYM * 3;                       // p16 + p8
 constexpr uint32_t E2_WIN = 372;                                    // staging words per warp (multiple of 4)
-constexpr size_t E2_SMEM = E2_PLANE_BYTES + (size_t)E2_WARPS * E2_WIN * 4;
+constexpr uint32_t E2_BAR = E2_PLANE_BYTES + E2_WARPS * E2_WIN * 4;    // the mbarrier of the plane load
+constexpr size_t E2_SMEM = E2_BAR + 16;
 constexpr uint32_t SCAN_PER_BLOCK = 4096;                           // groups per block of the first scan kernel
 constexpr unsigned long long NOT_FINAL = ~0ull;
 
@@ -84,14 +86,9 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
     extern __shared__ __align__(16) uint8_t s_len[];           // lenf plane, 64 KiB
     if (plan && plan->status) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(cb->lenf);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_len);
-        for (uint32_t i = tid; i < NSYM / 16; i += BITS_THREADS) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
     const uint32_t len_a = (uint32_t)__cvta_generic_to_shared(s_len);
+    cta_bulk_load(len_a, cb->lenf, NSYM, len_a + NSYM);        // one bulk copy; the mbarrier sits behind the plane
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
     const uint64_t warp0 = (uint64_t)blockIdx.x * (BITS_THREADS / 32) + (tid >> 5);
     const uint64_t nwarps = (uint64_t)gridDim.x * (BITS_THREADS / 32);
     for (uint64_t g = warp0; g < ngroups; g += nwarps) {
@@ -393,12 +390,10 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t *stage = reinterpret_cast<uint32_t *>(e2_smem + E2_PLANE_BYTES) + wid * E2_WIN;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(cb->p16);
-        uint4 *dst = reinterpret_cast<uint4 *>(e2_smem);
-        for (uint32_t i = tid; i < E2_PLANE_BYTES / 16; i += E2_THREADS) dst[i] = __ldg(src + i);
+    {   // p16 | p8 (192 KiB) by one bulk copy
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(e2_smem);
+        cta_bulk_load(a0, cb->p16, E2_PLANE_BYTES, a0 + E2_BAR);
     }
-    __syncthreads();
 
     // aligned frame: bit 0 of the frame is the 16-byte boundary at or below `stream`
     uint8_t *frame = reinterpret_cast<uint8_t *>((uintptr_t)stream & ~(uintptr_t)15);
@@ -583,11 +578,9 @@ enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Cod
     __shared__ uint32_t s_acc[BITS_THREADS / 32][IDX_SUBS_MAX];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(cb->lenf);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_len);
-        for (uint32_t i = tid; i < NSYM / 16; i += BITS_THREADS) dst[i] = __ldg(src + i);
+        const uint32_t len_a = (uint32_t)__cvta_generic_to_shared(s_len);
+        cta_bulk_load(len_a, cb->lenf, NSYM, len_a + NSYM);
     }
-    __syncthreads();
     const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
     const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
     uint32_t *acc = s_acc[wid];
@@ -729,7 +722,7 @@ int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Cod
     int rc = enc2_work(c, n_sym, &W, &ngroups, &nblocks);
     if (rc) return rc;
     if (!c->smem_attr[ATTR_INDEX]) {
-        HF_CUDA(c, cudaFuncSetAttribute(enc_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSYM));
+        HF_CUDA(c, cudaFuncSetAttribute(enc_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BITS_SMEM));
         c->smem_attr[ATTR_INDEX] = true;
     }
     d_stream += start_bit >> 3;
@@ -738,7 +731,7 @@ int launch_encode_index(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Cod
     const uint64_t bw = BITS_THREADS / 32;
     uint64_t grid = (ngroups + bw - 1) / bw;
     if (grid > (uint64_t)(3 * c->sm_count)) grid = 3 * c->sm_count;
-    HF_PROF(c, "enc_index_kernel"); enc_index_kernel<<<(unsigned)grid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, bit0, d_rec, n_subs);
+    HF_PROF(c, "enc_index_kernel"); enc_index_kernel<<<(unsigned)grid, BITS_THREADS, BITS_SMEM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, bit0, d_rec, n_subs);
     HF_LAUNCH_CHECK(c);
     return HF_OK;
 }
@@ -757,7 +750,7 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
 
     if (!c->smem_attr[ATTR_ENCODE]) {
         HF_CUDA(c, cudaFuncSetAttribute(encode2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM));
-        HF_CUDA(c, cudaFuncSetAttribute(enc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSYM));
+        HF_CUDA(c, cudaFuncSetAttribute(enc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BITS_SMEM));
         c->smem_attr[ATTR_ENCODE] = true;
     }
     // start_bit may exceed 8: fold whole bytes into the pointer
@@ -766,7 +759,7 @@ int launch_encode(Ctx *c, const uint8_t *d_in, uint64_t n_bytes, const Codebook 
     const uint64_t bw = BITS_THREADS / 32;
     uint64_t bgrid = (ngroups + bw - 1) / bw;
     if (bgrid > (uint64_t)(3 * c->sm_count)) bgrid = 3 * c->sm_count;
-    HF_PROF(c, "enc_bits_kernel"); enc_bits_kernel<<<(unsigned)bgrid, BITS_THREADS, NSYM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, plan);
+    HF_PROF(c, "enc_bits_kernel"); enc_bits_kernel<<<(unsigned)bgrid, BITS_THREADS, BITS_SMEM, c->stream>>>(d_in, n_sym, d_cb, W, ngroups, plan);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "enc_scan1_kernel"); enc_scan1_kernel<<<(unsigned)nblocks, 1024, 0, c->stream>>>(W, ngroups);
     HF_LAUNCH_CHECK(c);
