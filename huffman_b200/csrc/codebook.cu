@@ -26,12 +26,16 @@
 // Bytes moved are negligible (<= a few MB, L2 resident); the stage is latency bound and
 // reported in microseconds, not against the HBM roofline.
 #include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace hf {
 
 constexpr int CB_THREADS = 1024;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int SORT_BATCH = 8;                     // keys a lane loads ahead in the radix passes
+constexpr int SORT_BATCH = 8;                     // keys of a lane in a radix pass (tiles of 256 keys)
+constexpr int CB_CLUSTER = 8;                     // CTAs of the sorting cluster (the portable maximum; the scan below assumes 8)
 
 struct CbWork {
     unsigned long long keyA[NSYM], keyB[NSYM];      // counts (sort ping-pong); keyA ends as sorted leaf counts
@@ -41,6 +45,10 @@ struct CbWork {
     uint32_t entry_bits[NSYM];
     uint32_t U;
     uint32_t rounds;
+    // exchange areas of the sorting cluster
+    alignas(16) uint32_t cta_cnt[256 * CB_CLUSTER];           // keys per (digit, CTA) of a radix pass
+    uint32_t cta_nz[CB_CLUSTER];
+    unsigned long long cta_max[CB_CLUSTER];
 };
 
 size_t cb_work_bytes() { return sizeof(CbWork); }
@@ -100,52 +108,41 @@ __device__ __forceinline__ uint32_t block_count_le(const unsigned long long *a, 
 }
 
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CB_THREADS, 1)
+// A thread-block CLUSTER of CB_CLUSTER CTAs (one SM each) compacts and sorts; CTA 0 then builds the tree.  One SM
+// stores about one 32-byte sector per cycle, and a radix pass scatters every key to a sector of its own: one CTA
+// spent 0.21 of its 0.56 ms in the scatter stores of the four passes (clock64 per phase).  The CTAs exchange their
+// digit counts through global memory (L2) and meet at the hardware cluster barrier, twice per pass.
+__global__ void __cluster_dims__(CB_CLUSTER, 1, 1) __launch_bounds__(CB_THREADS, 1)
 cb_sort_tree_kernel(const unsigned long long *__restrict__ hist, CbWork *w, Codebook *cb)
 {
     __shared__ uint32_t s_scan[40];
-    __shared__ uint32_t s_cnt[32][256];             // warp-private digit counters / offsets
+    __shared__ uint32_t s_cnt[32][257];             // warp-private digit counters / offsets (padded: columns are read too)
+    __shared__ uint32_t s_base[256];                // where this CTA's keys of a digit start
     __shared__ unsigned long long s_u64[4];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t cta = cluster.block_rank();
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #ifdef CB_TIMING
     long long tq0 = clock64(), tq1 = 0, tq2 = 0, tqc = 0, tqs = 0, tqx = 0, tqa;
 #endif
 
     // ---- 1. compaction of the non-zero bins, symbol order (C:378-385, C:413-425) ----
-    // Coalesced: iteration j of the CTA reads bins [1024 j, 1024 j + 1024), a warp's 32 bins give one ballot mask; the
-    // masks' population counts are scanned in bin order (2,048 masks, two per thread) and the bins are read once more
-    // (L2) to be written at mask base + rank.  (One strip of 64 bins per thread made every load a sector of its own
-    // and every store wait for the load before it: 0.17 ms of the kernel's 0.56.)
-    constexpr uint32_t NIT = NSYM / CB_THREADS;     // 64
+    // CTA c takes bins [8192 c, 8192 c + 8192), coalesced: iteration j reads 1,024 of them, a warp's 32 bins give one
+    // ballot mask; the masks' population counts are scanned in bin order, the CTA totals are exchanged, and the bins
+    // are read once more (L2) to be written at CTA base + mask base + rank.
+    constexpr uint32_t NIT = NSYM / CB_THREADS / CB_CLUSTER;    // 8
     uint32_t *s_mask = &s_cnt[0][0];                // [NIT * 32] nonzero masks, index j * 32 + wid = bin order
     uint32_t *s_pref = s_mask + NIT * 32;           // their exclusive prefix
+    const uint32_t bin0 = cta * (NSYM / CB_CLUSTER);
     unsigned long long mx = 0;
-#pragma unroll 8
+    unsigned long long hv[NIT];
+#pragma unroll
     for (uint32_t j = 0; j < NIT; j++) {
-        const unsigned long long h = hist[j * CB_THREADS + tid];
-        mx = h > mx ? h : mx;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, h != 0);
+        hv[j] = hist[bin0 + j * CB_THREADS + tid];
+        mx = hv[j] > mx ? hv[j] : mx;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hv[j] != 0);
         if (lane == 0) s_mask[j * 32 + wid] = m;
     }
-    __syncthreads();
-    uint32_t U;
-    {
-        const uint32_t c0 = __popc(s_mask[2 * tid]), c1 = __popc(s_mask[2 * tid + 1]);
-        const uint32_t base = block_excl_scan_u32(c0 + c1, s_scan, &U);
-        s_pref[2 * tid] = base;
-        s_pref[2 * tid + 1] = base + c0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (uint32_t j = 0; j < NIT; j++) {
-        const unsigned long long h = hist[j * CB_THREADS + tid];
-        if (h) {
-            const uint32_t pos = s_pref[j * 32 + wid] + __popc(s_mask[j * 32 + wid] & ((1u << lane) - 1u));
-            w->keyA[pos] = h;
-            w->valA[pos] = j * CB_THREADS + tid;
-        }
-    }
-    // block max of the counts -> number of 8-bit digit passes
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
@@ -154,97 +151,135 @@ cb_sort_tree_kernel(const unsigned long long *__restrict__ hist, CbWork *w, Code
     if (tid == 0) s_u64[0] = 0;
     __syncthreads();
     if (lane == 0) atomicMax(&s_u64[0], mx);
-    __syncthreads();
-    mx = s_u64[0];
-    int passes = 0;
+    uint32_t nz_cta;
+    {
+        const uint32_t c0 = tid < NIT * 32 ? __popc(s_mask[tid]) : 0u;
+        const uint32_t base = block_excl_scan_u32(c0, s_scan, &nz_cta);        // (contains CTA barriers)
+        if (tid < NIT * 32) s_pref[tid] = base;
+    }
+    if (tid == 0) { w->cta_nz[cta] = nz_cta; w->cta_max[cta] = s_u64[0]; }
+    cluster.sync();
+    uint32_t U = 0, base_cta = 0;
+    mx = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < CB_CLUSTER; c++) {
+        const uint32_t n = w->cta_nz[c];
+        const unsigned long long m = w->cta_max[c];
+        base_cta += c < cta ? n : 0u;
+        U += n;
+        mx = m > mx ? m : mx;
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < NIT; j++) {
+        if (hv[j]) {
+            const uint32_t pos = base_cta + s_pref[j * 32 + wid] + __popc(s_mask[j * 32 + wid] & ((1u << lane) - 1u));
+            w->keyA[pos] = hv[j];
+            w->valA[pos] = bin0 + j * CB_THREADS + tid;
+        }
+    }
+    int passes = 0;                                 // 8-bit digit passes the largest count needs
     while (passes < 8 && (mx >> (8 * passes)) != 0) passes++;
-
+    cluster.sync();                                 // the keys are complete
 #ifdef CB_TIMING
     tq1 = clock64();
 #endif
+
     // ---- 2. stable LSD radix sort by count (C:387-389 semantics) ----
+    // 256 tiles (one per warp of the cluster) of `chunk` consecutive keys.  Stable order = digit, then tile: the CTAs
+    // exchange their counts per digit (2,048 numbers through L2), every CTA scans them in (digit, CTA) order, and
+    // the warps of a CTA share out the CTA's range of a digit in warp order; a warp then walks its tile in order.
     unsigned long long *kin = w->keyA, *kout = w->keyB;
     uint32_t *vin = w->valA, *vout = w->valB;
-    const uint32_t chunk = (((U + 31) / 32) + 31) & ~31u;      // keys per warp, multiple of 32
-    const uint32_t w_lo = min(U, wid * chunk), w_hi = min(U, (wid + 1) * chunk);
+    constexpr uint32_t NTILE = CB_CLUSTER * 32;
+    const uint32_t chunk = (((U + NTILE - 1) / NTILE) + 31) & ~31u;        // keys per tile, a multiple of 32 (<= 256)
+    const uint32_t tile = cta * 32 + wid;
+    const uint32_t w_lo = min(U, tile * chunk), w_hi = min(U, (tile + 1) * chunk);
     for (int p = 0; p < passes; p++) {
         const int sh = 8 * p;
-        for (uint32_t i = tid; i < 32 * 256; i += CB_THREADS) (&s_cnt[0][0])[i] = 0;
+        for (uint32_t i = tid; i < 32 * 257; i += CB_THREADS) (&s_cnt[0][0])[i] = 0;
         __syncthreads();
 #ifdef CB_TIMING
         tqa = clock64();
 #endif
-        // (eight loads in flight per lane, here and in the scatter)
-        for (uint32_t i0 = w_lo + lane; i0 < w_hi; i0 += 32 * SORT_BATCH) {
-            unsigned long long k8[SORT_BATCH];
+        unsigned long long k8[SORT_BATCH];          // my keys of the tile (<= 8 per lane), kept for the scatter
+        uint32_t v8[SORT_BATCH];
 #pragma unroll
-            for (int b = 0; b < SORT_BATCH; b++) k8[b] = i0 + 32 * b < w_hi ? kin[i0 + 32 * b] : 0ull;
-#pragma unroll
-            for (int b = 0; b < SORT_BATCH; b++)
-                if (i0 + 32 * b < w_hi) atomicAdd(&s_cnt[wid][(uint32_t)(k8[b] >> sh) & 255u], 1u);
+        for (int b = 0; b < SORT_BATCH; b++) {
+            const uint32_t i = w_lo + 32 * b + lane;
+            k8[b] = i < w_hi ? kin[i] : 0ull;
+            v8[b] = i < w_hi ? vin[i] : 0u;
         }
+#pragma unroll
+        for (int b = 0; b < SORT_BATCH; b++)
+            if (w_lo + 32 * b + lane < w_hi) atomicAdd(&s_cnt[wid][(uint32_t)(k8[b] >> sh) & 255u], 1u);
         __syncthreads();
+        if (tid < 256) {
+            uint32_t tot = 0;
+#pragma unroll 8
+            for (int q = 0; q < 32; q++) tot += s_cnt[q][tid];
+            w->cta_cnt[tid * CB_CLUSTER + cta] = tot;
+        }
+        cluster.sync();
 #ifdef CB_TIMING
         tqc += clock64() - tqa; tqa = clock64();
 #endif
-        // exclusive scan in (digit, warp) order: entry e = d * 32 + wrp; 8 entries per thread
-        uint32_t loc[8], sum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t e = tid * 8 + j;
-            loc[j] = s_cnt[e & 31][e >> 5];
-            sum += loc[j];
-        }
-        uint32_t run = block_excl_scan_u32(sum, s_scan, nullptr);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t e = tid * 8 + j;
-            s_cnt[e & 31][e >> 5] = run;
-            run += loc[j];
+        {
+            // entries 2 tid and 2 tid + 1 of the (digit, CTA) order: digit tid / 4, CTAs 2 (tid % 4) and + 1
+            const uint2 e = reinterpret_cast<const uint2 *>(w->cta_cnt)[tid];
+            const uint32_t run = block_excl_scan_u32(e.x + e.y, s_scan, nullptr);
+            if (cta == 2 * (tid & 3u)) s_base[tid >> 2] = run;
+            else if (cta == 2 * (tid & 3u) + 1) s_base[tid >> 2] = run + e.x;
         }
         __syncthreads();
-        // scatter, each warp walking its keys in order
+        if (tid < 256) {
+            uint32_t run = s_base[tid];
+#pragma unroll 8
+            for (int q = 0; q < 32; q++) { const uint32_t c = s_cnt[q][tid]; s_cnt[q][tid] = run; run += c; }
+        }
+        __syncthreads();
 #ifdef CB_TIMING
         tqs += clock64() - tqa; tqa = clock64();
 #endif
-        for (uint32_t g0 = w_lo; g0 < w_hi; g0 += 32 * SORT_BATCH) {
-            unsigned long long k8[SORT_BATCH];
-            uint32_t v8[SORT_BATCH];
+        // scatter, each warp walking its keys in order
 #pragma unroll
-            for (int b = 0; b < SORT_BATCH; b++) {
-                const uint32_t i = g0 + 32 * b + lane;
-                k8[b] = i < w_hi ? kin[i] : 0ull;
-                v8[b] = i < w_hi ? vin[i] : 0u;
+        for (int b = 0; b < SORT_BATCH; b++) {
+            const uint32_t i = w_lo + 32 * b + lane;
+            if (w_lo + 32 * b >= w_hi) break;       // uniform
+            const bool act = i < w_hi;
+            const unsigned long long k = k8[b];
+            const uint32_t d = (uint32_t)(k >> sh) & 255u;
+            // lanes with my digit: eight independent ballots; the first of them advances the warp's private counter
+            // and hands out the base
+            uint32_t peers = __ballot_sync(0xFFFFFFFFu, act);
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) {
+                const uint32_t bl = __ballot_sync(0xFFFFFFFFu, (d >> bit) & 1u);
+                peers &= ((d >> bit) & 1u) ? bl : ~bl;
             }
-#pragma unroll
-            for (int b = 0; b < SORT_BATCH; b++) {
-                const uint32_t i = g0 + 32 * b + lane;
-                if (g0 + 32 * b >= w_hi) break;     // uniform
-                const bool act = i < w_hi;
-                const unsigned long long k = k8[b];
-                const uint32_t d = (uint32_t)(k >> sh) & 255u;
-                const uint32_t amask = __ballot_sync(0xFFFFFFFFu, act);
-                if (act) {
-                    const uint32_t peers = __match_any_sync(amask, d);
-                    const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-                    const uint32_t pos = s_cnt[wid][d] + rank;
-                    __syncwarp(amask);
-                    if (rank == 0) s_cnt[wid][d] += __popc(peers);
-                    __syncwarp(amask);
-                    kout[pos] = k;
-                    vout[pos] = v8[b];
-                }
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+            uint32_t base = 0;
+            if (act && rank == 0) base = atomicAdd(&s_cnt[wid][d], __popc(peers));
+            base = __shfl_sync(0xFFFFFFFFu, base, act ? __ffs(peers) - 1 : lane);
+            if (act) {
+                kout[base + rank] = k;
+                vout[base + rank] = v8[b];
             }
         }
+        cluster.sync();                             // every key of the pass is in place
 #ifdef CB_TIMING
         tqx += clock64() - tqa;
 #endif
-        __syncthreads();
         unsigned long long *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
     // publish the order; keep the sorted counts in kin
-    for (uint32_t i = tid; i < U; i += CB_THREADS) cb->order[i] = (uint16_t)vin[i];
+    for (uint32_t i = cta * CB_THREADS + tid; i < U; i += CB_CLUSTER * CB_THREADS) {
+        cb->order[i] = (uint16_t)vin[i];
+        w->leafPar[i] = NONE;
+        w->intPar[i] = NONE;
+    }
+    cluster.sync();
+    if (cta != 0) return;                           // the tree is one CTA's
     const unsigned long long *leafF = kin;
     if (tid == 0) {
         w->U = U;
@@ -252,7 +287,6 @@ cb_sort_tree_kernel(const unsigned long long *__restrict__ hist, CbWork *w, Code
         // record which ping-pong buffer holds the sorted leaves for cb_codes_kernel
         w->rounds = (kin == w->keyA) ? 0u : 0x80000000u;
     }
-    for (uint32_t i = tid; i < U; i += CB_THREADS) { w->leafPar[i] = NONE; w->intPar[i] = NONE; }
     __syncthreads();
 
 #ifdef CB_TIMING
@@ -479,7 +513,7 @@ int launch_codebook(Ctx *c, const unsigned long long *d_hist, Codebook *d_cb)
     if (rc) return rc;
     CbWork *w = reinterpret_cast<CbWork *>(c->ws);
     HF_CUDA(c, cudaMemsetAsync(d_cb, 0, codebook_alloc_bytes(), c->stream));
-    HF_PROF(c, "cb_sort_tree_kernel"); cb_sort_tree_kernel<<<1, CB_THREADS, 0, c->stream>>>(d_hist, w, d_cb);
+    HF_PROF(c, "cb_sort_tree_kernel"); cb_sort_tree_kernel<<<CB_CLUSTER, CB_THREADS, 0, c->stream>>>(d_hist, w, d_cb);
     HF_LAUNCH_CHECK(c);
     HF_PROF(c, "cb_codes_kernel"); cb_codes_kernel<<<NSYM / 256, 256, 0, c->stream>>>(d_hist, w, d_cb);
     HF_LAUNCH_CHECK(c);
