@@ -339,7 +339,8 @@ static int compress_after_hist(Ctx *c, const uint8_t *d_in, uint64_t n, const ui
     if (total > capacity)
         return set_err(c, HF_ERR_CAPACITY, "hf_compress: need %llu bytes, capacity %llu", (unsigned long long)total,
                        (unsigned long long)capacity);
-    rc = hf_header_pack(ctx, cb, n, (n & 1) ? *h_last : 0, d_file, capacity);
+    // the image fits (total <= capacity): the worst-case header bound of the standalone stage call does not apply
+    rc = launch_header_pack(c, cb, n, (n & 1) ? *h_last : 0, nullptr, d_file, capacity, nullptr);
     if (rc) return rc;
     rc = launch_encode(c, d_in, n, cb, d_file + preamble_bytes(n), info.table_bits + 64, nullptr);
     if (rc || !d_index) return rc;

@@ -19,7 +19,7 @@
 //        nodes <= (sum of the two smallest) are paired in merged order, each pair found by
 //        a merge-path co-rank search (leaf queue first on ties); the new internal nodes
 //        come out already sorted.  Rounds ~ 20-50 for real data.
-//   2. cb_codes_kernel, one thread per leaf: walk to the root, emit len / code / enc32,
+//   2. cb_codes_kernel, one thread per leaf: walk to the root, emit len / code / the encoder's planes,
 //      reduce table_bits, payload_bits and maxlen.
 //   3. cb_entry_scan_kernel: exclusive scan of the header entry sizes (24 + len).
 //   4. header_pack_kernel, one thread per entry: OR the entry's bits into the image.

@@ -269,3 +269,26 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_clean_domain_predicate_is_pinned_from_both_sides(oracle):
+    """tests/golden/r1r2_trigger_check.json: the UNMODIFIED reference GPU compressor run on a B200 over 24 inputs of a
+    4-letter alphabet.  Every input the predicate calls clean gave the oracle's bytes; the inputs it
+    calls unclean differ from the ideal stream only in the first payload byte (R1) and / or the last byte (R2) — and
+    the predicate computed here is the one that was recorded there."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("r1r2", os.path.join(GOLDEN, "r1r2_trigger_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rec = json.load(open(os.path.join(GOLDEN, "r1r2_trigger_check.json")))
+    assert rec["clean_inputs_all_identical"] and rec["unclean_inputs_that_differ"] >= 10
+    for row in rec["rows"]:
+        data = mod.make_input(row["seed"])
+        assert hashlib.sha256(data.tobytes()).hexdigest() == row["input_sha256"]
+        assert oracle.reference_clean(data) == row["predicate_clean"]
+        image = oracle.compress(data)
+        assert image.size == row["image_bytes"] and mod.payload_start_byte(image) == row["first_payload_byte"]
+        if row["predicate_clean"]:
+            assert row["reference_equals_ideal"]
+        else:
+            assert row["only_first_payload_or_last_byte_differ"]

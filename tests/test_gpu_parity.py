@@ -232,6 +232,8 @@ def test_compress_capacity_is_the_image_size(codec, oracle):
                                small.numel(), ctypes.byref(size))
     assert rc == 3 and size.value == want.size
     assert np.array_equal(codec.compress(d).cpu().numpy(), want)         # the context carries on
+    got_i, _ = codec.compress_indexed(d, torch.empty(want.size, dtype=torch.uint8, device="cuda"))     # the indexed call likewise
+    assert np.array_equal(got_i.cpu().numpy(), want)
 
 
 def test_round_trip_fixtures(codec, romeo, jpeg):
@@ -783,3 +785,36 @@ def test_mixed_entropy_round_trip(codec):
     image = codec.compress(d)
     back = codec.decompress(image)
     assert back.numel() == n and torch.equal(back, d)
+
+
+@pytest.mark.gpu
+def test_write_kernels_split_and_agree(oracle, monkeypatch):
+    """the write stage is two kernels over disjoint chunks (long code words: dec_write3, short ones: dec_write4); each
+    of them alone, and the split, give the same bytes — on a stream that holds both kinds of chunk, with a head that is
+    not aligned and a tail that ends inside a chunk"""
+    from huffman_b200 import Codec
+    n = (6 * (4 << 20)) + 12346                                   # all six entropy classes, ragged end
+    d = synth.mixed(n, seg_bytes=4 << 20, device="cuda")
+    want = None
+    for mode in ("0", "3", "4"):
+        monkeypatch.setenv("HF_WRITE_KERNEL", mode)
+        c = Codec(0)
+        try:
+            image = c.compress(d)
+            if want is None:
+                want = image.clone()
+                assert np.array_equal(oracle.decompress(image.cpu().numpy()), d.cpu().numpy())
+            assert torch.equal(image, want)
+            c.profile(True)
+            back = c.decompress(image)
+            prof = c.profile_read()
+            c.profile(False)
+            assert torch.equal(back, d), mode
+            if mode == "0":
+                assert "dec_write3_kernel" in prof and "dec_write4_kernel" in prof
+            else:
+                assert ("dec_write3_kernel" in prof) == (mode == "3") and ("dec_write4_kernel" in prof) == (mode == "4")
+            out = torch.empty(n + 64, dtype=torch.uint8, device="cuda")     # an output that is only 2-byte aligned
+            assert torch.equal(c.decompress(image, out[2:2 + n]), d), mode
+        finally:
+            c.close()
