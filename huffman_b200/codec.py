@@ -78,9 +78,10 @@ class Codec:
     def launch_count(self):
         return int(self.lib.hf_launch_count(self.ctx))
 
-    def profile(self, on=True):
-        """bracket every kernel launch of this context with CUDA events (bench.py's roofline)"""
-        self._check(self.lib.hf_profile_enable(self.ctx, 1 if on else 0))
+    def profile(self, on=True, major_only=False):
+        """bracket every kernel launch of this context with CUDA events (bench.py's roofline); major_only: just the
+        kernels that move the data (an event pair costs a launch-bound sharded step ~5 us)"""
+        self._check(self.lib.hf_profile_enable(self.ctx, (2 if major_only else 1) if on else 0))
 
     def profile_read(self):
         """{kernel name: (launches, total device ms)} since the last read; synchronises"""

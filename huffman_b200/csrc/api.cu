@@ -37,9 +37,19 @@ int ensure_ws(Ctx *c, size_t bytes)
     return HF_OK;
 }
 
+// the kernels that move the data (a second profiling level times only these: an event pair costs ~5 us of a
+// launch-bound sequence of small kernels, 0.2 ms of a sharded step)
+static bool prof_major(const char *name)
+{
+    static const char *const major[] = {"hist_smem", "enc_bits", "encode2", "dec_sync4", "dec_write", "cb_sort_tree"};
+    for (const char *m : major) if (strncmp(name, m, strlen(m)) == 0) return true;
+    return false;
+}
+
 void prof_begin(Ctx *c, const char *name)
 {
     if (c->prof_n >= PROF_CAP) return;
+    if (c->prof_major_only && !prof_major(name)) return;
     c->prof_name[c->prof_n] = name;
     if (cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream) == cudaSuccess) c->prof_open = true;
 }
@@ -183,6 +193,7 @@ int hf_profile_enable(hf_ctx *ctx, int on)
         for (uint32_t i = 0; i < 2 * PROF_CAP; i++) HF_CUDA(c, cudaEventCreate(&c->prof_ev[i]));
     }
     c->prof_on = on != 0;
+    c->prof_major_only = on == 2;
     c->prof_open = false;
     c->prof_n = 0;
     return HF_OK;

@@ -162,6 +162,7 @@ struct Ctx {
     cudaEvent_t ring_ev[4];
     // optional per-kernel timing (hf_profile_*): event pairs around every launch
     bool prof_on;
+    bool prof_major_only;           // hf_profile_enable(ctx, 2): only the kernels that move the data
     bool prof_open;                 // a begin event is pending
     uint32_t prof_n;                // recorded pairs
     cudaEvent_t *prof_ev;           // 2 * PROF_CAP events, created on first enable

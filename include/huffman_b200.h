@@ -82,7 +82,8 @@ uint64_t hf_launch_count(hf_ctx *ctx);
 /* Per-kernel device times, for bench.py's roofline: while enabled, every kernel launch of this
  * context is bracketed by CUDA events on the context's stream (the reference prints wall
  * timers instead, C:356-399, C:492-593, h:697-698).  hf_profile_read synchronises, sums the
- * recorded launches by kernel name into out[0..*n_out) and clears the record. */
+ * recorded launches by kernel name into out[0..*n_out) and clears the record.  on = 1: every kernel; on = 2: only the
+ * kernels that move the data (histogram, unit bits, pack, synchronisation, write, codebook sort + tree). */
 typedef struct {
     char name[48];
     uint32_t launches;
