@@ -7,7 +7,7 @@
 // One process (or host thread) per GPU, one context each.  Every stage is enqueued on the context's stream and so are
 // the collectives (NCCL, loaded with dlopen so that the library has no link-time dependency and shares the copy a host
 // framework has already loaded); what the stages need from a collective — bit counts, hand-over bits — they read from
-// DEVICE memory, so a step has no host synchronisation between its first kernel and its last, and exactly four
+// DEVICE memory, so a step has no host synchronisation between its first kernel and its last, and exactly three
 // collectives each way:
 //   compress    all-reduce   65,536 x u64   the histogram                     (512 KiB)
 //               all-gather   1 x u64        payload bits of every shard       -> shard_plan_kernel: global start bits
