@@ -382,27 +382,37 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
             if (live) {
                 const uint32_t lw = min(lim, sub0 + SUB_BITS);
                 uint32_t n = 0;
-                while (pos < lw) {
-                    const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
-                    const uint32_t win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
-                    const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
-                    const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
-                    const bool micro = (e14 & 0xFu) != 0xCu;
-                    uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
-                    if (MULTI) {                        // all the code words the 14 bits hold, when they end inside the subsequence
-                        const uint32_t tot = (e14 >> 4) & 0xFu;
-                        if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
-                    }
-                    if (len == 0) {
+                // The inner loop runs for as long as the plane resolves the steps: an entry that does not (a code of more than
+                // 18 bits, a hole) has length 0 and ends it like the limit does, so the common step carries one test, not two
+                // (the separate `len == 0` branch was 4 of a step's 27 instructions).
+                if (pos < lw) {
+                    for (;;) {
+                        uint32_t len, win;
+                        do {
+                            const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
+                            win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
+                            const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
+                            const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
+                            const bool micro = (e14 & 0xFu) != 0xCu;
+                            len = micro ? deep : (e14 >> 28);
+                            uint32_t cnt = 1;
+                            if (MULTI) {                // all the code words the 14 bits hold, when they end inside the subsequence
+                                const uint32_t tot = (e14 >> 4) & 0xFu;
+                                if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
+                            }
+                            pos += len;
+                            n += cnt;                   // ("not here" counts one code word: the one resolved below)
+                        } while (len != 0 && pos < lw);
+                        if (len != 0) break;            // the limit
                         len = __ldg(S.tab->lenflat + (win >> k2shift));
                         if (len == 0) {
                             const uint32_t e = slow_decode(S.tab, S.frame, S.frame_bytes, span_bit0 + pos);
                             bad |= e >> 31;
                             len = e & 0x7Fu;
                         }
+                        pos += len;
+                        if (pos >= lw) break;
                     }
-                    pos += len;
-                    n += cnt;
                 }
                 sts16(rec_a + REC4_STRIDE * k, n ? ((rel & 63u) | (n << 6)) : 0u);
             }
