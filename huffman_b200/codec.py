@@ -173,7 +173,7 @@ class Codec:
 
     def range_overflow(self, buf, range_bytes, halo_bytes, table, result=None):
         """hf_range_overflow: device int64[4], [1] = bits by which the last code word that starts inside
-        buf[:range_bytes] runs past the range end (found speculatively from the last 16 KiB)"""
+        buf[:range_bytes] runs past the range end (found speculatively from the last 16 chunks = 256 KiB)"""
         if result is None:
             result = torch.zeros(4, dtype=torch.int64, device=self.device)
         self._check(self.lib.hf_range_overflow(self.ctx, _ptr(buf), range_bytes, halo_bytes, _ptr(table), _ptr(result)))

@@ -14,7 +14,7 @@ Compress
   5. all_gather of every slice's first 32 bytes and last byte: seam bytes are OR-merged and the
      bytes that follow a slice are kept behind it as read-ahead (`halo`) for the decoder
 Decompress (the format has no offset index: only rank 0 knows where its first code word starts)
-  1. each rank finds, by self-synchronising over the last 16 KiB of its byte range, where the first
+  1. each rank finds, by self-synchronising over its byte range (the stand-alone call hf_range_overflow: over the last 256 KiB), where the first
      code word AFTER its range starts                              -> all_gather(overflow, range bits)
   2. each rank decodes its range from its predecessor's overflow; the overflow it really ends with
      must confirm the speculated one                               -> all_gather(overflow, count, flags)
@@ -243,7 +243,7 @@ class ShardedCodec:
         dev = sl.buf.device
         my_bits = sl.range_bytes * 8
         # 1. where does the first code word after my range start?  (speculative: self-synchronisation over
-        #    the last 16 KiB of the range); every rank needs its predecessor's answer
+        #    the last 256 KiB of the range); every rank needs its predecessor's answer
         probe = st.range_overflow(sl.buf, sl.range_bytes, HALO, table) if sl.range_bytes else \
             torch.zeros(4, dtype=torch.int64, device=dev)
         mine = torch.stack([probe[1], torch.tensor(my_bits, dtype=torch.int64, device=dev)])
