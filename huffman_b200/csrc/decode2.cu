@@ -382,37 +382,27 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
             if (live) {
                 const uint32_t lw = min(lim, sub0 + SUB_BITS);
                 uint32_t n = 0;
-                // The inner loop runs for as long as the plane resolves the steps: an entry that does not (a code of more than
-                // 18 bits, a hole) has length 0 and ends it like the limit does, so the common step carries one test, not two
-                // (the separate `len == 0` branch was 4 of a step's 27 instructions).
-                if (pos < lw) {
-                    for (;;) {
-                        uint32_t len, win;
-                        do {
-                            const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
-                            win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
-                            const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
-                            const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
-                            const bool micro = (e14 & 0xFu) != 0xCu;
-                            len = micro ? deep : (e14 >> 28);
-                            uint32_t cnt = 1;
-                            if (MULTI) {                // all the code words the 14 bits hold, when they end inside the subsequence
-                                const uint32_t tot = (e14 >> 4) & 0xFu;
-                                if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
-                            }
-                            pos += len;
-                            n += cnt;                   // ("not here" counts one code word: the one resolved below)
-                        } while (len != 0 && pos < lw);
-                        if (len != 0) break;            // the limit
+                while (pos < lw) {
+                    const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
+                    const uint32_t win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
+                    const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
+                    const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
+                    const bool micro = (e14 & 0xFu) != 0xCu;
+                    uint32_t len = micro ? deep : (e14 >> 28), cnt = 1;
+                    if (MULTI) {                        // all the code words the 14 bits hold, when they end inside the subsequence
+                        const uint32_t tot = (e14 >> 4) & 0xFu;
+                        if (!micro && pos + tot <= lw) { len = tot; cnt = (e14 >> 8) & 0xFu; }
+                    }
+                    if (len == 0) {
                         len = __ldg(S.tab->lenflat + (win >> k2shift));
                         if (len == 0) {
                             const uint32_t e = slow_decode(S.tab, S.frame, S.frame_bytes, span_bit0 + pos);
                             bad |= e >> 31;
                             len = e & 0x7Fu;
                         }
-                        pos += len;
-                        if (pos >= lw) break;
                     }
+                    pos += len;
+                    n += cnt;
                 }
                 sts16(rec_a + REC4_STRIDE * k, n ? ((rel & 63u) | (n << 6)) : 0u);
             }
@@ -825,7 +815,10 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
 #endif
 constexpr int W4_THREADS = W4_WARPS * 32;
 constexpr uint32_t W4_LEAVES = 4u << MICRO_K;                   // offsets inside the dynamic shared memory
-constexpr uint32_t W4_RINGS = W4_LEAVES + NSYM * 2;             // a multiple of 1024
+#ifndef W4_LEAVES_BYTES
+#define W4_LEAVES_BYTES (NSYM * 2)
+#endif
+constexpr uint32_t W4_RINGS = W4_LEAVES + W4_LEAVES_BYTES;     // a multiple of 1024
 constexpr uint32_t W4_ROWS = W4_RINGS + W4_WARPS * 1024u;
 constexpr uint32_t W4_BAR = W4_ROWS + W4_WARPS * (ROW4_WORDS * ROW4_STRIDE);
 constexpr size_t W4_SMEM = W4_BAR + 16;
@@ -860,7 +853,7 @@ dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     const uint32_t ring_a = a0 + W4_RINGS + wid * 1024u + lane * 2u;
     const uint32_t row_a = a0 + W4_ROWS + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
     const uint32_t k2shift = 32u - tab->k2;
-    cta_bulk_load(a0, tab->t14, (4u << MICRO_K) + NSYM * 2, a0 + W4_BAR);     // t14 | leaves; the warps are on their own from here
+    cta_bulk_load(a0, tab->t14, (4u << MICRO_K) + W4_LEAVES_BYTES, a0 + W4_BAR);     // t14 | leaves; the warps are on their own from here
     uint32_t bad = 0;
     for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * W4_WARPS + wid; c < c1;
          c += (unsigned long long)gridDim.x * W4_WARPS) {

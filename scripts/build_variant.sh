@@ -9,7 +9,7 @@ mkdir -p "$dst/obj"
 for f in hist codebook encode2 decode decode2 sharded programs api; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c -o "$dst/obj/$f.o" "$root/huffman_b200/csrc/$f.cu" &
 done
-wait
+wait; for f in hist codebook encode2 decode decode2 sharded programs api; do test -f "$dst/obj/$f.o" || { echo "compile of $f.cu failed"; exit 1; }; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$dst/libhuffb200.so" "$dst"/obj/*.o -ldl
 rm -rf "$dst/obj"
 echo "built $dst/libhuffb200.so"
