@@ -106,6 +106,27 @@ def test_codebook_fuzz_ties(codec, oracle):
         check_codebook(codec, oracle, h)
 
 
+def test_codebook_cluster_sort_boundaries(codec, oracle):
+    """the compaction and the radix passes run on a cluster of 8 CTAs with tiles of ceil(U / 256) keys (multiples of
+    32) per warp: alphabet sizes around the tile, CTA and digit boundaries, symbols crowded into one CTA's bin range
+    or spread over all of them, tie-heavy and 40-bit counts (5 digit passes)"""
+    rng = np.random.default_rng(23)
+    sizes = [1, 2, 3, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 8191, 8192, 8193, 8224, 16385, 32767, 65535, 65536]
+    for t, U in enumerate(sizes):
+        h = np.zeros(65536, np.uint64)
+        if t % 3 == 0:
+            syms = np.arange(U)                                    # the lowest bins: the first CTAs only
+        elif t % 3 == 1:
+            syms = 65536 - 1 - np.arange(U)                        # the highest bins
+        else:
+            syms = rng.choice(65536, U, replace=False)
+        if t % 2 == 0:
+            h[syms] = rng.integers(1, 5, U)                        # tie-heavy: stability decides the order
+        else:
+            h[syms] = rng.integers(1, 1 << 40, U)                  # five digit passes
+        check_codebook(codec, oracle, h)
+
+
 def test_codebook_long_codes(codec, oracle):
     for n in (30, 45, 60):
         _, ocb = check_codebook(codec, oracle, fibonacci_hist(n))
