@@ -45,6 +45,8 @@ constexpr uint32_t SCAN_PER_BLOCK = 4096;                           // groups pe
 constexpr unsigned long long NOT_FINAL = ~0ull;
 
 __device__ __forceinline__ uint32_t fold16(uint32_t sym) { return sym ^ (sym >> 8); }      // involution on 16 bits
+// the same for the two symbols of a 32-bit input word at once: two instructions instead of four
+__device__ __forceinline__ uint32_t fold16x2(uint32_t w) { return w ^ ((w >> 8) & 0x00FF00FFu); }
 
 // shared-memory loads by 32-bit shared address (taken once with __cvta_generic_to_shared)
 __device__ __forceinline__ uint32_t lds8(uint32_t a)
@@ -106,7 +108,7 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
                 const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 uint32_t t = 0;
 #pragma unroll
-                for (int i = 0; i < 8; i++) t += lds8(len_a + fold16(w8[i] & 0xFFFFu)) + lds8(len_a + fold16(w8[i] >> 16));
+                for (int i = 0; i < 8; i++) { const uint32_t f2 = fold16x2(w8[i]); t += lds8(len_a + (f2 & 0xFFFFu)) + lds8(len_a + (f2 >> 16)); }
                 t = __reduce_add_sync(0xFFFFFFFFu, t);
                 if (lane == u) mine = t;
                 a = na; b = nb;
@@ -372,6 +374,9 @@ __device__ __noinline__ void encode_unit_general(const UnitCtx &C, uint64_t unit
             }
         }
         __syncwarp();                                       // the window is reused
+        // leave it zero, as the inlined path expects to find it
+        for (uint32_t i = lane; i < (used + 3) / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
     }
 }
 
@@ -390,6 +395,9 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t *stage = reinterpret_cast<uint32_t *>(e2_smem + E2_PLANE_BYTES) + wid * E2_WIN;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    // a warp's window is zero between units: the flush of a unit puts zeros back where it read (one store per vector
+    // that leaves anyway, instead of a zeroing loop and a warp barrier before every pack)
+    for (uint32_t i = lane; i < E2_WIN / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
     {   // p16 | p8 (192 KiB) by one bulk copy
         const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(e2_smem);
         cta_bulk_load(a0, cb->p16, E2_PLANE_BYTES, a0 + E2_BAR);
@@ -447,12 +455,12 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 uint32_t zero = 0xFFFFFFFFu;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    const uint32_t sj = (j & 1) ? (w8[j >> 1] >> 16) : (w8[j >> 1] & 0xFFFFu);
-                    const uint32_t f = fold16(sj);
+                    const uint32_t f2 = fold16x2(w8[j >> 1]);
+                    const uint32_t f = (j & 1) ? (f2 >> 16) : (f2 & 0xFFFFu);
                     const uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
                     v[j] = x;
                     zero = min(zero, x);
-                    L += 31 - __clz(x | 1u);
+                    L += 31 - __clz(x);                 // (x = 0: the unit takes the general path and L is not used)
                 }
                 if (__any_sync(0xFFFFFFFFu, zero == 0)) fast = false;   // a code longer than 23 bits
                 if (fast) {
@@ -473,9 +481,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, o); if (lane >= o) off += y; }
             off -= L;                                               // unit bits before my first symbol
 
-            // ---- zero the window words that will be used, pack ----
-            for (uint32_t i = lane; i < (own_hi + 4) / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
+            // ---- pack (the window is zero: see the flush below) ----
             {
                 uint32_t pos = phase + off;
 #pragma unroll
@@ -534,8 +540,11 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             __syncwarp();
             // ---- my words leave: 128-bit stores where a whole group is mine, else single words ----
             const unsigned long long G0 = (gbit - phase) >> 5;      // frame word of window word 0 (multiple of 4)
+            // (my first bits may sit in the word before own_lo, which the unit before me completes and stores: vector 0)
+            if (lane == 0 && (own_lo >> 2) != 0) reinterpret_cast<uint4 *>(stage)[0] = make_uint4(0, 0, 0, 0);
             for (uint32_t q = (own_lo >> 2) + lane; q <= (own_hi >> 2); q += 32) {
                 uint4 o = reinterpret_cast<const uint4 *>(stage)[q];
+                reinterpret_cast<uint4 *>(stage)[q] = make_uint4(0, 0, 0, 0);
                 o.x = bswap32(o.x); o.y = bswap32(o.y); o.z = bswap32(o.z); o.w = bswap32(o.w);
                 const uint32_t w0 = 4 * q;
                 if (w0 >= own_lo && w0 + 3 <= own_hi) {
