@@ -481,9 +481,16 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, o); if (lane >= o) off += y; }
             off -= L;                                               // unit bits before my first symbol
 
-            // ---- pack (the window is zero: see the flush below) ----
+            // ---- pack (the window is zero: see the flush below).  A lane strings its 16 codes together in registers:
+            // pairs of codes are appended to the bits pending in `acc` (`fill` of them, left aligned; the leading
+            // `pos & 31` bits of a lane's first word belong to the lanes before it and stay zero), and every word that
+            // fills up leaves with a plain store — the lane that holds a word's LAST bit is the only one that stores
+            // it.  What is left at the end (less than a word) is OR-ed in after the stores: one shared-memory atomic
+            // per lane and unit instead of three per pair of codes. ----
             {
-                uint32_t pos = phase + off;
+                const uint32_t pos = phase + off;
+                uint32_t fill = pos & 31, acc = 0;
+                uint32_t *wp = stage + (pos >> 5);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const uint32_t x0 = v[j], x1 = v[j + 1];
@@ -492,13 +499,18 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     const uint32_t b32 = __funnelshift_lc(0u, x1, 32 - l1);
                     const uint32_t hi = a32 | (b32 >> l0);                    // l0 <= 23
                     const uint32_t lo = __funnelshift_r(0u, b32, l0);
-                    const uint32_t LL = l0 + l1, sh = pos & 31;
-                    const uint32_t sa = sbase + 4u * (pos >> 5);
-                    red_or_if(LL != 0, sa, hi >> sh);
-                    red_or_if(sh + LL > 32, sa + 4, __funnelshift_r(lo, hi, sh));
-                    red_or_if(sh + LL > 64, sa + 8, __funnelshift_r(0u, lo, sh));
-                    pos += LL;
+                    const uint32_t nf = fill + l0 + l1;                       // < 32 + 46
+                    const uint32_t w0 = acc | (hi >> fill);
+                    const uint32_t w1 = __funnelshift_r(lo, hi, fill);
+                    const uint32_t w2 = __funnelshift_r(0u, lo, fill);
+                    if (nf >= 32) wp[0] = w0;
+                    if (nf >= 64) wp[1] = w1;
+                    acc = nf >= 64 ? w2 : (nf >= 32 ? w1 : w0);
+                    wp += nf >> 5;
+                    fill = nf & 31;
                 }
+                __syncwarp();
+                red_or_if(fill != 0, (uint32_t)__cvta_generic_to_shared(wp), acc);
             }
             __syncwarp();
             // ---- my last, partial word is completed with the codes that follow (the next unit's first symbols): lanes
