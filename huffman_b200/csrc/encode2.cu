@@ -209,6 +209,22 @@ __device__ __forceinline__ void red_or_if(bool p, uint32_t saddr, uint32_t v)
                  :: "r"((uint32_t)p), "r"(saddr), "r"(v) : "memory");
 }
 
+// position of the leading one (0xFFFFFFFF for 0): one FLO instead of FLO + a subtraction from 31
+__device__ __forceinline__ uint32_t bfind32(uint32_t x)
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// stores w0 at shared address `a` when nf >= 32 and w1 behind it when nf >= 64, without a branch
+__device__ __forceinline__ void sts_if_full(uint32_t nf, uint32_t a, uint32_t w0, uint32_t w1)
+{
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ge.u32 p, %0, 32;\n\tsetp.ge.u32 q, %0, 64;\n\t"
+                 "@p st.shared.u32 [%1], %2;\n\t@q st.shared.u32 [%1+4], %3;\n\t}"
+                 :: "r"(nf), "r"(a), "r"(w0), "r"(w1) : "memory");
+}
+
 // (len, code) of one symbol from the shared planes, or from the global codebook when it is not there
 __device__ __forceinline__ void lookup_any(const uint16_t *p16, const uint8_t *p8, const Codebook *cb, uint32_t sym,
                                            uint32_t &len, unsigned long long &code)
@@ -460,7 +476,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     const uint32_t x = (uint32_t)p16[f] | ((uint32_t)p8[f] << 16);
                     v[j] = x;
                     zero = min(zero, x);
-                    L += 31 - __clz(x);                 // (x = 0: the unit takes the general path and L is not used)
+                    L += bfind32(x);                    // (x = 0: the unit takes the general path and L is not used)
                 }
                 if (__any_sync(0xFFFFFFFFu, zero == 0)) fast = false;   // a code longer than 23 bits
                 if (fast) {
@@ -490,11 +506,11 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             {
                 const uint32_t pos = phase + off;
                 uint32_t fill = pos & 31, acc = 0;
-                uint32_t *wp = stage + (pos >> 5);
+                uint32_t wa = sbase + 4u * (pos >> 5);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const uint32_t x0 = v[j], x1 = v[j + 1];
-                    const uint32_t l0 = 31 - __clz(x0), l1 = 31 - __clz(x1);
+                    const uint32_t l0 = bfind32(x0), l1 = bfind32(x1);
                     const uint32_t a32 = __funnelshift_lc(0u, x0, 32 - l0);   // left aligned, the leading one falls off
                     const uint32_t b32 = __funnelshift_lc(0u, x1, 32 - l1);
                     const uint32_t hi = a32 | (b32 >> l0);                    // l0 <= 23
@@ -503,14 +519,13 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     const uint32_t w0 = acc | (hi >> fill);
                     const uint32_t w1 = __funnelshift_r(lo, hi, fill);
                     const uint32_t w2 = __funnelshift_r(0u, lo, fill);
-                    if (nf >= 32) wp[0] = w0;
-                    if (nf >= 64) wp[1] = w1;
+                    sts_if_full(nf, wa, w0, w1);
                     acc = nf >= 64 ? w2 : (nf >= 32 ? w1 : w0);
-                    wp += nf >> 5;
+                    wa += (nf >> 5) << 2;
                     fill = nf & 31;
                 }
                 __syncwarp();
-                red_or_if(fill != 0, (uint32_t)__cvta_generic_to_shared(wp), acc);
+                red_or_if(fill != 0, wa, acc);
             }
             __syncwarp();
             // ---- my last, partial word is completed with the codes that follow (the next unit's first symbols): lanes
