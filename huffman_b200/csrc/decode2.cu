@@ -309,7 +309,11 @@ constexpr uint32_t REC4_WORDS = LANE_SUBS / 2;                  // 16 u16 record
 constexpr uint32_t ROW4_STRIDE = 32 * 4;                        // bytes between consecutive words of a lane
 constexpr uint32_t REC4_STRIDE = 32 * 2;                        // bytes between consecutive records of a lane
 constexpr uint32_t S4_TAB_BYTES = 4u << MICRO_K;                // the d14 plane
-constexpr uint32_t S4_BAR = S4_TAB_BYTES + S4_THREADS * (ROW4_WORDS + REC4_WORDS) * 4;    // the mbarrier of the plane load
+// dec_sync4's rows are RINGS of two subsequences (words 0-7: the even ones, 8-15: the odd ones, 16: a copy of word 0):
+// the word that follows a subsequence is the first word of the next one, which the lane has already stored, so a
+// subsequence is ONE 32-byte load — a whole sector, read once — instead of two halves and a look-ahead word
+constexpr uint32_t S4_ROW_WORDS = 2 * (SUB_BITS / 32) + 1;
+constexpr uint32_t S4_BAR = S4_TAB_BYTES + S4_THREADS * (S4_ROW_WORDS + REC4_WORDS) * 4;    // the mbarrier of the plane load
 constexpr size_t S4_SMEM = S4_BAR + 16;
 static_assert(GROUP_CHUNKS == 1, "dec_sync4: a warp converges on one chunk");
 
@@ -348,6 +352,33 @@ __device__ __forceinline__ void load_sub_raw4(uint4 &a, uint4 &d, uint32_t &next
     if (b + 32 < frame_bytes) next = __ldg(reinterpret_cast<const uint32_t *>(frame + b + 32));
 }
 
+// the 32 bytes of the frame at byte b (one sector), as loaded; zero past the end.  a32: the frame is 32-byte aligned
+// (one 256-bit load; otherwise two halves)
+__device__ __forceinline__ void load_sub8(uint32_t (&r)[8], const uint8_t *frame, unsigned long long frame_bytes,
+                                          unsigned long long b, bool a32)
+{
+    if (a32 && b + 32 <= frame_bytes) {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "l"(frame + b));
+    } else {
+        uint4 a = make_uint4(0, 0, 0, 0), d = a;
+        if (b < frame_bytes) a = ld_stream_v4(frame + b);
+        if (b + 16 < frame_bytes) d = ld_stream_v4(frame + b + 16);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = d.w;
+    }
+}
+// registers -> one half of the lane's ring (big-endian words); the even half leaves a copy of its first word behind word 15
+__device__ __forceinline__ void store_half(uint32_t row_a, uint32_t odd, const uint32_t (&r)[8])
+{
+    const uint32_t ha = row_a + odd * (8u * ROW4_STRIDE);
+    const uint32_t w0 = bswap32(r[0]);
+    sts32(ha, w0);
+#pragma unroll
+    for (int i = 1; i < 8; i++) sts32(ha + i * ROW4_STRIDE, bswap32(r[i]));
+    if (!odd) sts32(row_a + 16u * ROW4_STRIDE, w0);
+}
+
 // The lanes with `live` set walk their spans from bit `wstart` (relative to the span) up to `lim`, writing one
 // record per subsequence into their record rows.  have_rec: the row describes an earlier walk of this span; the
 // new walk stops at the first subsequence it enters where the earlier one did and keeps the earlier records (and
@@ -359,20 +390,25 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
     const uint32_t d14_a = S.d14_a, k2shift = S.k2shift;
     const unsigned long long span_byte0 = span_bit0 >> 3;
     uint32_t pos = wstart;
-    uint4 na, nd;
-    uint32_t nnext = 0;
-    if (live) load_sub_raw4(na, nd, nnext, S.frame, S.frame_bytes, span_byte0);
+    const bool a32 = ((uintptr_t)S.frame & 31) == 0;
+    uint32_t r[8];                                      // the subsequence in flight
+    if (live) {
+        load_sub8(r, S.frame, S.frame_bytes, span_byte0, a32);
+        store_half(row_a, 0u, r);
+        load_sub8(r, S.frame, S.frame_bytes, span_byte0 + 32u, a32);
+    }
 #pragma unroll 1
     for (uint32_t k = 0; k < LANE_SUBS; k++) {
         if (!__any_sync(0xFFFFFFFFu, live)) break;
         if (live) {
-            // my subsequence k: registers -> row (big-endian words); the next one goes in flight
-            sts32(row_a + 0 * ROW4_STRIDE, bswap32(na.x)); sts32(row_a + 1 * ROW4_STRIDE, bswap32(na.y));
-            sts32(row_a + 2 * ROW4_STRIDE, bswap32(na.z)); sts32(row_a + 3 * ROW4_STRIDE, bswap32(na.w));
-            sts32(row_a + 4 * ROW4_STRIDE, bswap32(nd.x)); sts32(row_a + 5 * ROW4_STRIDE, bswap32(nd.y));
-            sts32(row_a + 6 * ROW4_STRIDE, bswap32(nd.z)); sts32(row_a + 7 * ROW4_STRIDE, bswap32(nd.w));
-            sts32(row_a + 8 * ROW4_STRIDE, bswap32(nnext));
-            if (k + 1 < LANE_SUBS) load_sub_raw4(na, nd, nnext, S.frame, S.frame_bytes, span_byte0 + 32ull * (k + 1));
+            // subsequence k + 1 has arrived (after the last one: the first word of the next span): into the other
+            // half of the ring, behind subsequence k; k + 2 goes in flight
+            store_half(row_a, (k + 1) & 1u, r);
+            if (k + 2 < LANE_SUBS) load_sub8(r, S.frame, S.frame_bytes, span_byte0 + 32ull * (k + 2), a32);
+            else if (k + 2 == LANE_SUBS) {
+                const unsigned long long b = span_byte0 + 32ull * LANE_SUBS;
+                r[0] = b < S.frame_bytes ? __ldg(reinterpret_cast<const uint32_t *>(S.frame + b)) : 0u;
+            }
             const uint32_t sub0 = SUB_BITS * k;
             const uint32_t rel = pos - sub0;            // where this walk enters the subsequence (< 64 for codes <= 64 bits)
             if (have_rec && pos < lim) {                // entering where the earlier walk did: the walks have met
@@ -383,7 +419,7 @@ __device__ __forceinline__ void walk_lane(const Sync4Ctx &S, uint32_t row_a, uin
                 const uint32_t lw = min(lim, sub0 + SUB_BITS);
                 uint32_t n = 0;
                 while (pos < lw) {
-                    const uint32_t wa = row_a + ((pos << 2) & (7u * ROW4_STRIDE));      // word (pos / 32) mod 8 of my row
+                    const uint32_t wa = row_a + ((pos << 2) & (15u * ROW4_STRIDE));     // word (pos / 32) mod 16 of my ring
                     const uint32_t win = __funnelshift_l(lds32(wa + ROW4_STRIDE), lds32(wa), pos);
                     const uint32_t e14 = lds32(d14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
                     const uint32_t deep = (MICRO_K + 1) + ((e14 >> ((win >> (32 - MICRO_MAX - 1)) & 30u)) & 3u);  // micro tree: 2 bits per slot
@@ -514,8 +550,8 @@ __device__ __forceinline__ void sync4_setup(uint32_t *smem, const DecodeTable *t
     d14_a = opaque_shared_addr(smem);
     cta_bulk_load(d14_a, tab->d14, S4_TAB_BYTES, d14_a + S4_BAR);          // lengths only; one bulk copy, no per-thread staging
     const uint32_t wid = tid >> 5, lane = tid & 31;
-    row_a = d14_a + S4_TAB_BYTES + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
-    rec_a = d14_a + S4_TAB_BYTES + S4_WARPS * (ROW4_WORDS * ROW4_STRIDE) + wid * (LANE_SUBS * REC4_STRIDE) + lane * 2u;
+    row_a = d14_a + S4_TAB_BYTES + wid * (S4_ROW_WORDS * ROW4_STRIDE) + lane * 4u;
+    rec_a = d14_a + S4_TAB_BYTES + S4_WARPS * (S4_ROW_WORDS * ROW4_STRIDE) + wid * (LANE_SUBS * REC4_STRIDE) + lane * 2u;
 }
 
 __global__ void __launch_bounds__(S4_THREADS, 1)
