@@ -274,6 +274,15 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void *p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// The 32 bytes at p (a whole sector) as two 128-bit halves.  wide: p is 32-byte aligned — ONE 256-bit load (sm_100:
+// LDG.E.256), so a warp whose lanes read 32 bytes each touches every sector once instead of once per half.
+__device__ __forceinline__ void ld_stream_2v4(const void *p, bool wide, uint4 &a, uint4 &b)
+{
+    if (wide)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    else { a = ld_stream_v4(p); b = ld_stream_v4(reinterpret_cast<const uint8_t *>(p) + 16); }
+}
 __device__ __forceinline__ void st_stream_v4(void *p, uint4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"

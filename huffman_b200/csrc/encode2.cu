@@ -172,7 +172,7 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t len_a = (uint32_t)__cvta_generic_to_shared(s_len);
     cta_bulk_load(len_a, cb->lenf, NSYM, len_a + NSYM);        // one bulk copy; the mbarrier sits behind the plane
-    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0, wide = ((uintptr_t)in_bytes & 31) == 0;
     unsigned long long pend_g = 0;                                  // counted and published, its start not summed up yet
     bool have_pend = false;
     const uint64_t nblocks = (ngroups + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -192,11 +192,12 @@ enc_bits_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Code
             // looked up, and there is no per-symbol end test (a predicated lookup makes the compiler rebuild the
             // shared base address for every symbol)
             const uint8_t *src = in_bytes + (g * GROUP_SYMS + lane * 16) * 2;
-            uint4 a = ld_stream_v4(src), b = ld_stream_v4(src + 16);
+            uint4 a, b;
+            ld_stream_2v4(src, wide, a, b);
 #pragma unroll 4
             for (uint32_t u = 0; u < GROUP_UNITS; u++) {
                 uint4 na = a, nb = b;
-                if (u + 1 < GROUP_UNITS) { na = ld_stream_v4(src + (u + 1) * (UNIT_SYMS * 2)); nb = ld_stream_v4(src + (u + 1) * (UNIT_SYMS * 2) + 16); }
+                if (u + 1 < GROUP_UNITS) ld_stream_2v4(src + (u + 1) * (UNIT_SYMS * 2), wide, na, nb);
                 if (u == GROUP_UNITS - 4) {
                     if (have_pend) pend_d = scan_peek(W, pend_g, lane);
                 }
@@ -461,7 +462,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
     uint8_t *frame = reinterpret_cast<uint8_t *>((uintptr_t)stream & ~(uintptr_t)15);
     uint32_t *gw = reinterpret_cast<uint32_t *>(frame);
     const unsigned long long bit0 = ((uintptr_t)stream & 15) * 8ull + start_bit;   // first payload bit, frame coordinates
-    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0, wide = ((uintptr_t)in_bytes & 31) == 0;
     const uint64_t nunits = (n_sym + UNIT_SYMS - 1) / UNIT_SYMS;
     const UnitCtx C{in_bytes, n_sym, nunits, cb, p16, p8, stage, sbase, frame, bit0, aligned};
 
@@ -503,7 +504,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
             if (fast) {
                 if (!have_cur) {
                     const uint8_t *src = gin + u * (UNIT_SYMS * 2);
-                    cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
+                    ld_stream_2v4(src, wide, cur0, cur1);
                 }
                 const uint32_t w8[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
                 uint32_t zero = 0xFFFFFFFFu;
@@ -521,7 +522,7 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                     // my symbols are codes now: their registers take the next unit's symbols, which arrive while this
                     // unit is packed; the next unit's first 16, one per lane, complete my last word
                     const uint8_t *src = gin + (u + 1) * (UNIT_SYMS * 2);
-                    cur0 = ld_stream_v4(src); cur1 = ld_stream_v4(src + 16);
+                    ld_stream_2v4(src, wide, cur0, cur1);
                     tail_sym = *reinterpret_cast<const uint16_t *>(src - (int)(lane * 32) + (int)((lane & 15) * 2));
                 }
             }
@@ -655,7 +656,7 @@ enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Cod
         const uint32_t len_a = (uint32_t)__cvta_generic_to_shared(s_len);
         cta_bulk_load(len_a, cb->lenf, NSYM, len_a + NSYM);
     }
-    const bool aligned = ((uintptr_t)in_bytes & 15) == 0;
+    const bool aligned = ((uintptr_t)in_bytes & 15) == 0, wide = ((uintptr_t)in_bytes & 31) == 0;
     const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
     uint32_t *acc = s_acc[wid];
     const uint64_t warp0 = (uint64_t)blockIdx.x * (BITS_THREADS / 32) + wid;
@@ -681,10 +682,10 @@ enc_index_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Cod
                 uint4 c0 = nx0, c1 = nx1;
                 if (!have_nx) {
                     const uint8_t *src = in_bytes + (unit * UNIT_SYMS + lane * 16) * 2;
-                    c0 = ld_stream_v4(src); c1 = ld_stream_v4(src + 16);
+                    ld_stream_2v4(src, wide, c0, c1);
                 }
                 const uint8_t *nsrc = in_bytes + ((unit + 1) * UNIT_SYMS + lane * 16) * 2;
-                nx0 = ld_stream_v4(nsrc); nx1 = ld_stream_v4(nsrc + 16);
+                ld_stream_2v4(nsrc, wide, nx0, nx1);
                 have_nx = true;
                 const uint32_t w8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
