@@ -685,6 +685,10 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     DecLayout L(work, nch);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint16_t *sout = s_leaves + NSYM + wid * (WIN + 8);                         // this warp's window
+    // the planes and the window by 32-bit shared address: a compare, an add and the address of a look-up are one
+    // instruction each instead of the two or three of a generic 64-bit pointer
+    const uint32_t t14_a = opaque_shared_addr(w3_smem), lv_a = t14_a + (4u << MICRO_K);
+    const uint32_t sout_a = lv_a + NSYM * 2u + wid * ((WIN + 8) * 2u);
     if (dense_min != 0xFFFFFFFFu) {     // every chunk of this CTA is dec_write4_kernel's: leave before the planes load
         const unsigned long long upc = (DEC_THREADS / 32) / upw;                // runs per chunk
         bool any = false;
@@ -756,8 +760,8 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
             const uint32_t wend = min((uint32_t)total, w0 + WIN);
             const uint32_t o_end = min(my_end, wend);
             if (o < o_end) {
-                uint16_t *sp = sout + (o - w0 + mis);
-                uint16_t *const sp_end = sout + (o_end - w0 + mis);
+                uint32_t sp = sout_a + 2u * (o - w0 + mis);
+                const uint32_t sp_end = sout_a + 2u * (o_end - w0 + mis);
                 // phases of W3_PHASE words: the window's two words are picked by selects inside a phase; longer
                 // phases keep more lanes busy (a lane leaves a phase when its position passes the phase's end)
 #pragma unroll
@@ -769,12 +773,12 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         for (int k = 1; k < W3_PHASE; k++)
                             if (pos >= 32u * (w + k)) { hi = r[w + k]; lo = r[w + k + 1]; }
                         const uint32_t win = __funnelshift_l(lo, hi, pos);
-                        const uint32_t e14 = s_t14[win >> (32 - MICRO_K)];
+                        const uint32_t e14 = lds32(t14_a + ((win >> (30 - MICRO_K)) & ((4u << MICRO_K) - 4u)));
                         uint32_t len, sym;
                         if (e14 & MICRO_FLAG) {
                             uint32_t leaf;
                             micro_decode(e14, win, len, leaf);
-                            sym = s_leaves[leaf];
+                            sym = lds16(lv_a + 2u * leaf);
                         } else {
                             len = (e14 >> 1) & 0x7Fu;
                             sym = e14 >> 16;
@@ -788,7 +792,8 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                                 sym = (e >> 8) & 0xFFFFu;
                             }
                         }
-                        *sp++ = (uint16_t)sym;
+                        sts16(sp, sym);
+                        sp += 2;
                         pos += len;
                     }
                 }
