@@ -274,6 +274,25 @@ __device__ __forceinline__ void lookup_any(const uint16_t *p16, const uint8_t *p
     else { len = cb->len[sym]; code = cb->code[sym]; }
 }
 
+// One lane completes a partial word — `have` bits of it are there — with the codes of the symbols from sx on (any code
+// length; the input may end first).
+__device__ __forceinline__ uint32_t complete_word(const uint16_t *p16, const uint8_t *p8, const Codebook *cb, const uint8_t *in_bytes,
+                                                  uint64_t n_sym, uint64_t sx, uint32_t have, uint32_t word)
+{
+    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
+    for (; have < 32 && sx < n_sym; sx++) {
+        uint32_t len;
+        unsigned long long code;
+        lookup_any(p16, p8, cb, in16[sx], len, code);
+        if (len) {
+            const unsigned long long left = code << (64 - len);    // left aligned
+            word |= (uint32_t)(left >> 32) >> have;
+            have += len;
+        }
+    }
+    return word;
+}
+
 // OR `len` bits of `code` (right aligned) into the window at window bit `pos`; words outside [0, E2_WIN) of the
 // window that starts at window word `wbase` are dropped.  Any length up to 64.
 __device__ __forceinline__ void put_code_slow(uint32_t sbase, uint32_t wbase, uint32_t pos, unsigned long long code,
@@ -485,19 +504,33 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
         const uint8_t *gin = in_bytes + (unit0 * UNIT_SYMS + lane * 16) * 2;
         const bool first_group = g == 0;
         uint32_t slow = 0;                                      // units of the group that take the general path
+        // Between two consecutive units of the common case the last, partial word of the first is CARRIED: lane 0 takes
+        // it out of the window and starts the next unit's first word with it, so the word leaves with the unit that
+        // holds its last bit.  Everywhere else (the group's ends, units of the general path) a word belongs to the unit
+        // that holds its FIRST bit, which completes it with the codes that follow.
+        bool carry_in = false;                                  // warp-uniform: lane 0 holds the word before my first bit in cw
+        uint32_t cw = 0;
         for (uint32_t u = 0; u < nu; u++) {
             const uint32_t bits = __shfl_sync(0xFFFFFFFFu, ub, u);
             const unsigned long long gbit = gstart + __shfl_sync(0xFFFFFFFFu, ux, u);  // unit's first bit, frame coordinates
             const uint32_t phase = (uint32_t)(gbit & 127);
-            // words I own: those whose first bit is mine (the first unit also owns the word the stream starts in)
+            // words I own: those whose first bit is mine (the first unit also owns the word the stream starts in, a unit
+            // with a carried word the word it starts in)
             const bool first_unit = first_group && u == 0;
-            const uint32_t own_lo = first_unit ? (phase >> 5) : ((phase + 31) >> 5);
+            const uint32_t own_lo = (first_unit || carry_in) ? (phase >> 5) : ((phase + 31) >> 5);
             const uint32_t end_rel = phase + bits;                  // window bit after my last bit
-            const uint32_t own_hi = bits ? ((end_rel - 1) >> 5) : 0u;
-            if (!(bits > 0 && own_hi >= own_lo)) { have_cur = false; continue; }   // my bits sit in a word the unit before me completes
-
+            uint32_t own_hi = bits ? ((end_rel - 1) >> 5) : 0u;
+            bool fast = bits > 0 && own_hi >= own_lo;               // (else my bits sit in a word the unit before me completes)
             // the common case: whole units of an aligned input, this one and the next, away from the stream's ends
-            bool fast = aligned && !first_unit && u < fast_end && end_rel <= E2_WIN * 32;
+            fast = fast && aligned && !first_unit && u < fast_end && end_rel <= E2_WIN * 32;
+            // will my last word be carried?  the next unit must be one of the common case too (but for a code longer than
+            // 23 bits, which only its look-ups show: it completes the carried word the slow way then)
+            const uint32_t have0 = end_rel & 31;                    // bits of my last word that are mine
+            bool carry_out = false;
+            if (have0 && u + 1 < nu && u + 1 < fast_end) {
+                const uint32_t nbits = __shfl_sync(0xFFFFFFFFu, ub, u + 1);
+                carry_out = nbits >= 64 && (end_rel & 127u) + nbits <= E2_WIN * 32;
+            }
             uint32_t v[16];
             uint32_t L = 0;
             uint32_t tail_sym = 0;
@@ -520,14 +553,20 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 if (__any_sync(0xFFFFFFFFu, zero == 0)) fast = false;   // a code longer than 23 bits
                 if (fast) {
                     // my symbols are codes now: their registers take the next unit's symbols, which arrive while this
-                    // unit is packed; the next unit's first 16, one per lane, complete my last word
+                    // unit is packed; the next unit's first 16, one per lane, complete my last word when it is not carried
                     const uint8_t *src = gin + (u + 1) * (UNIT_SYMS * 2);
                     ld_stream_2v4(src, wide, cur0, cur1);
-                    tail_sym = *reinterpret_cast<const uint16_t *>(src - (int)(lane * 32) + (int)((lane & 15) * 2));
+                    if (!carry_out) tail_sym = *reinterpret_cast<const uint16_t *>(src - (int)(lane * 32) + (int)((lane & 15) * 2));
                 }
             }
             if (!fast) {                                            // left for the loop below: a call in this loop makes
-                slow |= 1u << u;                                    // the compiler keep the loop's state in local memory
+                if (carry_in) {                                     // the compiler keep the loop's state in local memory
+                    // the word carried to me after all belongs to the unit before me: completed by one lane, from the input
+                    if (lane == 0)
+                        gw[gbit >> 5] = bswap32(complete_word(p16, p8, cb, in_bytes, n_sym, (unit0 + u) * UNIT_SYMS, phase & 31u, cw));
+                    carry_in = false;
+                }
+                if (bits > 0 && own_hi >= ((first_unit ? phase : phase + 31) >> 5)) slow |= 1u << u;
                 have_cur = false;
                 continue;
             }
@@ -538,13 +577,13 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
 
             // ---- pack (the window is zero: see the flush below).  A lane strings its 16 codes together in registers:
             // pairs of codes are appended to the bits pending in `acc` (`fill` of them, left aligned; the leading
-            // `pos & 31` bits of a lane's first word belong to the lanes before it and stay zero), and every word that
-            // fills up leaves with a plain store — the lane that holds a word's LAST bit is the only one that stores
-            // it.  What is left at the end (less than a word) is OR-ed in after the stores: one shared-memory atomic
-            // per lane and unit instead of three per pair of codes. ----
+            // `pos & 31` bits of a lane's first word belong to the lanes before it and stay zero — or are the carried
+            // word's, in lane 0), and every word that fills up leaves with a plain store — the lane that holds a word's
+            // LAST bit is the only one that stores it.  What is left at the end (less than a word) is OR-ed in after the
+            // stores: one shared-memory atomic per lane and unit instead of three per pair of codes. ----
             {
                 const uint32_t pos = phase + off;
-                uint32_t fill = pos & 31, acc = 0;
+                uint32_t fill = pos & 31, acc = carry_in ? cw : 0u;     // (cw is zero in every lane but lane 0)
                 uint32_t wa = sbase + 4u * (pos >> 5);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
@@ -567,10 +606,13 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 red_or_if(fill != 0, wa, acc);
             }
             __syncwarp();
-            // ---- my last, partial word is completed with the codes that follow (the next unit's first symbols): lanes
-            // 0-15 look one symbol up each and OR their code in where it starts inside the word ----
-            const uint32_t have0 = end_rel & 31;                    // bits of my last word that are mine
-            if (have0) {
+            // ---- my last, partial word: carried to the next unit, or completed with the codes that follow (the next
+            // unit's first symbols): lanes 0-15 look one symbol up each and OR their code in where it starts inside the word ----
+            cw = 0;
+            if (carry_out) {
+                if (lane == 0) { cw = stage[own_hi]; stage[own_hi] = 0; }
+                own_hi--;                                           // (a unit of the common case has at least 16 words)
+            } else if (have0) {
                 uint32_t x = 0, l = 0;
                 if (lane < 16) {
                     const uint32_t f = fold16(tail_sym);
@@ -588,21 +630,10 @@ encode2_kernel(const uint8_t *__restrict__ in_bytes, uint64_t n_sym, const Codeb
                 } else if (lane == 0) {
                     // long codes, or sixteen one- and two-bit codes that do not fill the word: one lane, from the input;
                     // the next unit is whole, so the word does fill up before the input ends
-                    uint32_t have = have0, word = 0;
-                    const uint16_t *in16 = reinterpret_cast<const uint16_t *>(in_bytes);
-                    for (uint64_t sx = (unit0 + u + 1) * UNIT_SYMS; have < 32 && sx < n_sym; sx++) {
-                        uint32_t len;
-                        unsigned long long code;
-                        lookup_any(p16, p8, cb, in16[sx], len, code);
-                        if (len) {
-                            const unsigned long long left = code << (64 - len);    // left aligned
-                            word |= (uint32_t)(left >> 32) >> have;
-                            have += len;
-                        }
-                    }
-                    stage[own_hi] |= word;
+                    stage[own_hi] = complete_word(p16, p8, cb, in_bytes, n_sym, (unit0 + u + 1) * UNIT_SYMS, have0, stage[own_hi]);
                 }
             }
+            carry_in = carry_out;
             __syncwarp();
             // ---- my words leave: 128-bit stores where a whole group is mine, else single words ----
             const unsigned long long G0 = (gbit - phase) >> 5;      // frame word of window word 0 (multiple of 4)
