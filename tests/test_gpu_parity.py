@@ -690,6 +690,36 @@ def test_encode_units_larger_than_the_staging_window(codec, oracle):
         assert np.array_equal(dec.cpu().numpy().view(np.uint16), data)
 
 
+def test_encode_sparse_long_codes(codec, oracle):
+    # mostly symbols with short codes and, every ~1,500 symbols, one whose code is longer than the 23 bits the
+    # encoder's shared-memory table holds: units of the common case and units of the general path alternate, so the
+    # partial word a common-case unit hands on in a register meets a unit that cannot take it (completed the slow
+    # way), and the other way round
+    h = fibonacci_hist(45)
+    syms = np.flatnonzero(h).astype(np.uint16)
+    ocb = oracle.codebook(h)
+    _, o_len, o_code = ocb.arrays()
+    order = syms[np.argsort(o_len[syms].astype(np.int64), kind="stable")]
+    short, rare = order[:6], order[-6:]
+    assert o_len[short].max() <= 8 and o_len[rare].min() > 23
+    rng = np.random.default_rng(17)
+    data = rng.choice(short, 300000).astype(np.uint16)
+    at = np.cumsum(rng.integers(700, 2300, 190))
+    data[at[at < data.size]] = rng.choice(rare, int((at < data.size).sum()))
+    bitstr = "".join(format(int(o_code[s]), "b").zfill(int(o_len[s])) for s in data)
+    cb = codec.build_codebook(dev(h.astype(np.int64)))
+    table = codec.decode_table_from_codebook(cb)
+    for start_bit in (0, 6):
+        want = np.packbits(np.frombuffer(("0" * start_bit + bitstr).encode(), np.uint8) - ord("0"))
+        out = torch.zeros(want.size + 64, dtype=torch.uint8, device="cuda")
+        codec.encode(dev(data.view(np.uint8)), cb, out, start_bit)
+        assert np.array_equal(out.cpu().numpy()[: want.size], want), start_bit
+        dec = torch.empty(data.size * 2, dtype=torch.uint8, device="cuda")
+        codec.decode(out, start_bit, data.size, table, dec)
+        codec.sync()
+        assert np.array_equal(dec.cpu().numpy().view(np.uint16), data)
+
+
 def test_long_runs_do_not_resynchronise(codec, oracle):
     # A long run of one byte pair is a periodic bit pattern: a walk that enters it out of phase leaves it out of
     # phase, so the guessed chains of the decoder's groups never meet the true one inside the run.  Runs from a
