@@ -854,16 +854,17 @@ dec_write3_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
 //     the two partial vectors at the ends of a lane's run (once per 4096 bits) leave a symbol at a time;
 //   * the planes arrive by bulk copies (cp.async.bulk + mbarrier), the payload by 32-byte loads one subsequence ahead.
 // Nothing is shared between lanes after the offset scan: no barrier of any kind inside the chunk loop.
-// Shared memory: t14 64 KiB | leaves 128 KiB | rings 1 KiB per warp | rows 1152 B per warp | the mbarrier.
+// Shared memory: t14 64 KiB | rings 1 KiB per warp | rows 1152 B per warp | the mbarrier.  The leaves of the micro trees
+// (code words of 15-18 bits, rare in the chunks this kernel takes) are read through L1 instead: without their 128 KiB
+// there is room for 32 warps, and this kernel is bound by latency (16 warps beside the leaves: 2.08 ms on 4 GiB of the
+// mixed stream; leaves through L1: 16 warps 2.34, 24 warps 1.94, 32 warps 1.82).  A second plane with the SECOND code
+// word a window holds (two symbols per look-up) was built and measured: 1.82 -> 1.82 / 1.85 (the lanes of a warp leave a
+// subsequence together, and the extra look-up and the shorter blocks between flush tests cost what the pairs save).
 #ifndef W4_WARPS
-#define W4_WARPS 16
+#define W4_WARPS 32
 #endif
 constexpr int W4_THREADS = W4_WARPS * 32;
-constexpr uint32_t W4_LEAVES = 4u << MICRO_K;                   // offsets inside the dynamic shared memory
-#ifndef W4_LEAVES_BYTES
-#define W4_LEAVES_BYTES (NSYM * 2)
-#endif
-constexpr uint32_t W4_RINGS = W4_LEAVES + W4_LEAVES_BYTES;     // a multiple of 1024
+constexpr uint32_t W4_RINGS = 4u << MICRO_K;                    // behind the t14 plane; offsets inside the dynamic shared memory
 constexpr uint32_t W4_ROWS = W4_RINGS + W4_WARPS * 1024u;
 constexpr uint32_t W4_BAR = W4_ROWS + W4_WARPS * (ROW4_WORDS * ROW4_STRIDE);
 constexpr size_t W4_SMEM = W4_BAR + 16;
@@ -894,11 +895,11 @@ dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
     const unsigned long long head_sub = F0 / SUB_BITS;  // the subsequence that holds the first code word
     const uint32_t head_pos = (uint32_t)(F0 % SUB_BITS);
     DecLayout L(work, nch);
-    const uint32_t t14_a = a0, lv_a = a0 + W4_LEAVES;
+    const uint32_t t14_a = a0;
     const uint32_t ring_a = a0 + W4_RINGS + wid * 1024u + lane * 2u;
     const uint32_t row_a = a0 + W4_ROWS + wid * (ROW4_WORDS * ROW4_STRIDE) + lane * 4u;
     const uint32_t k2shift = 32u - tab->k2;
-    cta_bulk_load(a0, tab->t14, (4u << MICRO_K) + W4_LEAVES_BYTES, a0 + W4_BAR);     // t14 | leaves; the warps are on their own from here
+    cta_bulk_load(a0, tab->t14, 4u << MICRO_K, a0 + W4_BAR);       // t14 only (see above); the warps are on their own from here
     uint32_t bad = 0;
     for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * W4_WARPS + wid; c < c1;
          c += (unsigned long long)gridDim.x * W4_WARPS) {
@@ -962,7 +963,7 @@ dec_write4_kernel(const uint8_t *__restrict__ frame, unsigned long long frame_by
                         if (e14 & MICRO_FLAG) {
                             uint32_t leaf;
                             micro_decode(e14, win, len, leaf);
-                            sym = lds16(lv_a + 2u * leaf);
+                            sym = __ldg(tab->leaves + leaf);       // rare in these chunks: through L1, not in shared memory
                         } else {
                             len = (e14 >> 1) & 0x7Fu;
                             sym = e14 >> 16;
