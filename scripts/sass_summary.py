@@ -1,5 +1,5 @@
 """Instruction-class counts per kernel from the SASS of the built library (cuobjdump -sass), for profiles/sass_summary.txt:
-which kernels use bulk copies (UBLKCP) and mbarriers (SYNCS), the cluster barrier (UCGABAR / BAR.*CGA), shared-memory
+which kernels use bulk copies (UBLKCP) and mbarriers (SYNCS), 256-bit global loads (LDG.256, sm_100), the cluster barrier (UCGABAR / BAR.*CGA), shared-memory
 atomics, local memory.     python scripts/sass_summary.py > profiles/sass_summary.txt"""
 import collections
 import os
@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "huffman_b200", "libhuffb200.so")
 CLASSES = [("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"), ("UCGABAR", r"\bUCGABAR|\bCGABAR|BAR\.[A-Z.]*CGA"), ("CCTL", r"\bCCTL"),
            ("ATOMS", r"\bATOMS"), ("ATOMG/RED", r"\bATOMG|\bATOM\b|\bRED\b"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"),
-           ("LDG", r"\bLDG"), ("STG", r"\bSTG"), ("LDL", r"\bLDL"), ("STL", r"\bSTL"), ("BAR", r"\bBAR\."),
+           ("LDG", r"\bLDG"), ("LDG.256", r"\bLDG\.[A-Z0-9.]*256"), ("STG", r"\bSTG"), ("LDL", r"\bLDL"), ("STL", r"\bSTL"), ("BAR", r"\bBAR\."),
            ("SHFL", r"\bSHFL"), ("VOTE", r"\bVOTE"), ("MATCH", r"\bMATCH"), ("FLO/POPC/BREV", r"\bFLO|\bPOPC|\bBREV"),
            ("R2UR/REDUX", r"\bREDUX"), ("UTMA*", r"\bUTMALDG|\bUTMASTG")]
 
