@@ -7,23 +7,25 @@
 // Work is cut into UNITS of 512 symbols (1 KiB of input, 16 symbols per lane) and GROUPS of 32 units.
 //   enc_bits_kernel     bits of every unit (u32) and of every group, from the 64 KiB length plane in shared
 //                       memory.  Reads N, writes N / 256.
-//                       The group totals are scanned in the same pass (decoupled look-back over the groups,
-//                       lookback_scan): a group's start bit is known when its warp leaves.
+//                       The group totals are scanned in the same pass (decoupled look-back on two levels,
+//                       scan_publish / scan_resolve): every group's start bit is known when the kernel ends.
 //   encode2_kernel      one persistent CTA per SM, 20 warps, the 192 KiB code table (24-bit entries in two planes,
 //                       index XOR-folded against bank conflicts) in shared memory.  Every WARP packs groups on its
 //                       own: unit start = group start + a shuffle scan of the 32 unit counts; the lanes look their
-//                       16 codes up, a shuffle scan of the lane totals gives the lane's bit offset, pairs of codes
-//                       are merged in registers and OR-ed into the warp's zeroed staging window (predicated
-//                       red.shared, no divergence), and the window leaves with aligned 128-bit stores.  A 32-bit
+//                       16 codes up, a shuffle scan of the lane totals gives the lane's bit offset, a lane strings its
+//                       codes together in registers and stores every 32-bit word that fills up into the warp's zeroed
+//                       staging window (plain predicated stores; one red.shared per lane for the leftover), and the
+//                       window leaves with aligned 128-bit stores.  Between two units of the common case the partial
+//                       last word is carried in a register to the unit that holds its last bit; elsewhere a 32-bit
 //                       word belongs to the unit that holds its first bit: the owner completes its last, partial
-//                       word by encoding the symbols that FOLLOW the unit, so units exchange nothing and there is
+//                       word by encoding the symbols that FOLLOW the unit, so groups exchange nothing and there is
 //                       no CTA barrier after the table is loaded.  Reads N, writes C.
 // Codes longer than 23 bits (not in the shared table) and units whose bits exceed the staging window take a
 // slow per-symbol path through the global codebook.
 // Bits before the start phase in the first byte are preserved (they belong to the header or to the previous shard,
 // C:541, C:294-310); the last byte is zero padded (C:597-601).
 //
-// Algorithmic bytes: N read + C written (traffic 2N + C + N/128).  Roofline: HBM; today issue / LSU bound.
+// Algorithmic bytes: N read + C written (traffic 2N + C + N/128).  Roofline: HBM; today bound by shared-memory look-ups / issue.
 #include "common.cuh"
 
 namespace hf {
