@@ -196,6 +196,9 @@ def test_compress_pdf_standin_and_unaligned_output(codec, oracle):
     for off in (1, 5, 13, 16):
         got = codec.compress(d, buf[off:])
         assert np.array_equal(got.cpu().numpy(), want), off
+        # ... and decompress from there: the decoder's frame is 16-byte aligned but not 32-byte aligned at offset 16
+        # (two 128-bit loads per subsequence instead of one 256-bit load), and starts mid-vector at the odd offsets
+        assert torch.equal(codec.decompress(got), d), off
 
 
 def test_encode_long_codes(codec, oracle):
