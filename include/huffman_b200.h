@@ -134,7 +134,8 @@ int hf_header_pack(hf_ctx *ctx, const void *d_codebook, uint64_t n_bytes, uint32
                    uint8_t *d_file, uint64_t capacity);
 
 /* C:50-74 + C:541-588 + C:597-601 (populateCWLength, scan, encodeFromCW, tail flush):
- * bits per 512-symbol unit, a two-level scan, one warp-independent packing kernel.  Writes the code words of the byte pairs of
+ * bits per 512-symbol unit with their scan in the same pass (decoupled look-back), one warp-independent packing kernel.
+ * Writes the code words of the byte pairs of
  * d_in[0 .. n_bytes & ~1) as one MSB-first bit stream starting `start_bit` bits after
  * d_stream.  Bits of the first byte before the start phase are preserved (they belong to
  * the header or to the previous shard); the final partial byte is zero padded. */
