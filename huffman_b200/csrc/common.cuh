@@ -169,8 +169,10 @@ struct Ctx {
     const char **prof_name;         // PROF_CAP static strings
 };
 enum { ATTR_HIST = 0, ATTR_ENCODE, ATTR_PARSE, ATTR_SYNC, ATTR_WRITE, ATTR_INDEX, ATTR_WRITE4 };
-// chunks (16 KiB of payload) with this many code words or more (under ~9 bits each) are written by dec_write4_kernel
-constexpr uint32_t WRITE_SPLIT_DEFAULT = 131072 / 9;
+// chunks (16 KiB of payload) with this many code words or more (under ~11 bits each) are written by dec_write4_kernel.
+// (Measured with its 32 warps: the 1 GiB Zipf(1.2) stream, 10.6 bits per code word under its own codebook, 3.22 -> 2.27 ms
+// with it; the text class of the mixed stream, 11.3 bits, is faster in dec_write3_kernel: 1.37 against ~1.7 ms per GiB.)
+constexpr uint32_t WRITE_SPLIT_DEFAULT = 131072 / 11;
 constexpr uint32_t PROF_CAP = 8192;
 constexpr uint32_t PIPE_SLOTS = 4096;
 constexpr uint32_t SCAN_BLOCKS_MAX = 1u << 16;  // x 4096 chunks x 16 KiB = 4 TiB of payload
